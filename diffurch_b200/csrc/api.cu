@@ -1,0 +1,780 @@
+// C ABI of the B200 ensemble integrator (include/diffurch_b200.h).
+//
+// Host side of the drop-in boundary: validates the POD problem descriptor (the
+// flattened `Solver` builder state, reference src/solver.rs:65-76), owns the
+// device memory behind the opaque handle, and dispatches to the compiled
+// kernel for (system, tableau shape/sparsity, arithmetic, feature set).
+// There is NO CPU execution path here: without a CUDA device dfb_create fails.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/diffurch_b200.h"
+#include "dev/common.cuh"
+#include "host/tableaux.hpp"
+#include "launch.hpp"
+
+// OdeFixedArgs is declared per arithmetic namespace in dev/ode_fixed.cuh; the
+// two definitions are layout-identical.  Pull both in through small shims.
+namespace dfb_strict {
+int run_ode_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h,
+                       size_t n, const double* y0, const double* params, double* t_final,
+                       double* y_final, unsigned long long* steps, unsigned long long* rhs_evals,
+                       uint32_t* status, cudaStream_t stream);
+}
+namespace dfb_fast {
+int run_ode_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h,
+                       size_t n, const double* y0, const double* params, double* t_final,
+                       double* y_final, unsigned long long* steps, unsigned long long* rhs_evals,
+                       uint32_t* status, cudaStream_t stream);
+}
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+#define DFB_CUDA(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return fail(DFB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));       \
+  } while (0)
+
+struct SysInfo {
+  int id, n_state, n_params, n_aux, n_detectors, n_callbacks, uses_history;
+};
+const SysInfo kSystems[] = {
+    {DFB_SYS_LORENZ, 3, 3, 0, 0, 0, 0},
+    {DFB_SYS_LORENZ_VARIATIONAL, 12, 3, 3, 0, 1, 0},
+    {DFB_SYS_LINEAR1, 1, 1, 1, 0, 1, 0},
+    {DFB_SYS_LINEAR1_SIN, 1, 1, 1, 0, 1, 0},
+    {DFB_SYS_LINEAR3, 3, 9, 0, 0, 0, 0},
+    {DFB_SYS_LINEAR3_MATRIX, 9, 9, 3, 0, 2, 0},
+    {DFB_SYS_HARMONIC, 2, 0, 0, 0, 0, 0},
+    {DFB_SYS_POWER_DECAY, 1, 0, 0, 0, 0, 0},
+    {DFB_SYS_CONSTANT3, 3, 0, 0, 0, 0, 0},
+    {DFB_SYS_TIME3, 3, 0, 0, 0, 0, 0},
+    {DFB_SYS_ZERO1, 1, 0, 0, 1, 0, 0},
+    {DFB_SYS_DDE_LINEAR, 1, 4, 0, 0, 0, 1},
+    {DFB_SYS_NDDE_LINEAR, 1, 4, 0, 0, 0, 1},
+    {DFB_SYS_BOUNCING_BALL, 2, 2, 0, 2, 1, 0},
+    {DFB_SYS_EGG_BILLIARD, 4, 1, 1, 1, 1, 0},
+    {DFB_SYS_RELAY_MSIGN, 2, 0, 0, 1, 0, 0},
+    {DFB_SYS_DDE_RELAY_CLAMP, 2, 3, 0, 1, 0, 1},
+};
+const SysInfo* find_system(int id) {
+  for (const SysInfo& s : kSystems)
+    if (s.id == id) return &s;
+  return nullptr;
+}
+
+// ---- layout kernels: caller-facing array-of-states <-> device structure-of-arrays
+__global__ void aos_to_soa_kernel(const double* __restrict__ src, double* __restrict__ dst,
+                                  size_t n, int width) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int c = 0; c < width; ++c) dst[size_t(c) * n + i] = src[i * width + c];
+}
+__global__ void soa_to_aos_kernel(const double* __restrict__ src, double* __restrict__ dst,
+                                  size_t n, int width) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int c = 0; c < width; ++c) dst[i * width + c] = src[size_t(c) * n + i];
+}
+
+// ---- FP64 peak microbenchmark: 8 independent DFMA chains per thread
+__global__ void __launch_bounds__(256) dfma_chain_kernel(double* out, int iters, double a, double b,
+                                                         long long* cycles) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+         x6 = x0 + 6, x7 = x0 + 7;
+  const long long c0 = clock64();
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x0 = fma(x0, a, b);
+      x1 = fma(x1, a, b);
+      x2 = fma(x2, a, b);
+      x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b);
+      x5 = fma(x5, a, b);
+      x6 = fma(x6, a, b);
+      x7 = fma(x7, a, b);
+    }
+  }
+  const long long c1 = clock64();
+  out[size_t(blockIdx.x) * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *cycles = c1 - c0;
+}
+
+size_t next_pow2(size_t v) {
+  size_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace
+
+struct dfb_handle {
+  dfb_problem prob;
+  SysInfo info;
+  size_t n = 0;
+  int device = 0;
+  int ring_capacity = 0;
+  bool uses_disco = false;
+  bool has_initial = false, has_params = false, ran = false;
+  // inputs
+  double *d_y0 = nullptr, *d_params = nullptr;
+  const double *d_y0_ext = nullptr, *d_params_ext = nullptr;
+  double* d_stage = nullptr;  // AoS staging, n * max(width)
+  size_t stage_width = 0;
+  // outputs
+  double *d_t = nullptr, *d_y = nullptr, *d_aux = nullptr;
+  unsigned long long *d_steps = nullptr, *d_rejected = nullptr, *d_events = nullptr,
+                     *d_rhs = nullptr;
+  uint32_t* d_status = nullptr;
+  double *d_trace_t = nullptr, *d_trace_y = nullptr;
+  uint32_t* d_nsamples = nullptr;
+  double* d_ev_t = nullptr;
+  int32_t* d_ev_idx = nullptr;
+  uint32_t* d_nevents = nullptr;
+  double *d_ring_t = nullptr, *d_ring_y = nullptr, *d_ring_k = nullptr;
+  double* d_disco_t = nullptr;
+  int32_t* d_disco_ord = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t stream = nullptr;
+  unsigned launches = 0;
+  int locate_batch = 12;
+  bool used_hot_path = false;
+};
+
+namespace {
+
+template <class T>
+cudaError_t dalloc(T** p, size_t count) {
+  return cudaMalloc(reinterpret_cast<void**>(p), (count ? count : 1) * sizeof(T));
+}
+
+void free_all(dfb_handle* h) {
+  cudaSetDevice(h->device);
+  void* ptrs[] = {h->d_y0,      h->d_params,  h->d_stage,    h->d_t,       h->d_y,
+                  h->d_aux,     h->d_steps,   h->d_rejected, h->d_events,  h->d_rhs,
+                  h->d_status,  h->d_trace_t, h->d_trace_y,  h->d_nsamples, h->d_ev_t,
+                  h->d_ev_idx,  h->d_nevents, h->d_ring_t,   h->d_ring_y,  h->d_ring_k,
+                  h->d_disco_t, h->d_disco_ord};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+}
+
+int validate(const dfb_problem& p, const SysInfo** info_out) {
+  if (p.abi_version != DFB_ABI_VERSION) return fail(DFB_ERR_INVALID, "abi_version mismatch");
+  const SysInfo* info = find_system(p.system_id);
+  if (!info) return fail(DFB_ERR_INVALID, "unknown system_id");
+  const dfb_tableau& rk = p.rk;
+  if (rk.S < 1 || rk.S > DFB_MAX_STAGES || rk.I < 1 || rk.I > DFB_MAX_INTERP)
+    return fail(DFB_ERR_INVALID, "tableau shape out of range");
+  if (p.arith != DFB_ARITH_STRICT && p.arith != DFB_ARITH_FAST)
+    return fail(DFB_ERR_INVALID, "arith");
+  if (p.stepsize_kind != DFB_STEP_FIXED && p.stepsize_kind != DFB_STEP_AUTOMATIC)
+    return fail(DFB_ERR_INVALID, "stepsize_kind");
+  if (p.stepsize_kind == DFB_STEP_FIXED && !(p.h > 0.0)) return fail(DFB_ERR_INVALID, "h must be > 0");
+  if (p.n_loc < 0 || p.n_loc > DFB_MAX_LOCATORS) return fail(DFB_ERR_INVALID, "n_loc");
+  if (p.n_disco < 0 || p.n_disco > DFB_MAX_DISCO) return fail(DFB_ERR_INVALID, "n_disco");
+  if (p.history_id < DFB_HIST_CONSTANT || p.history_id > DFB_HIST_INV_SQUARE)
+    return fail(DFB_ERR_INVALID, "history_id");
+  if ((p.history_id == DFB_HIST_SIN || p.history_id == DFB_HIST_SIN_NODERIV) && info->n_params < 4)
+    return fail(DFB_ERR_INVALID, "sin history needs a system with parameter k (index 3)");
+  if (std::isnan(p.t0) || std::isnan(p.t1)) return fail(DFB_ERR_INVALID, "interval");
+  for (int l = 0; l < p.n_loc; ++l) {
+    const dfb_locator& L = p.loc[l];
+    if (L.kind < DFB_LOC_STATEFN || L.kind > DFB_LOC_PROPAGATION)
+      return fail(DFB_ERR_INVALID, "locator kind");
+    if (L.kind == DFB_LOC_STATEFN) {
+      if (L.detection < DFB_DET_ZERO || L.detection > DFB_DET_STEP)
+        return fail(DFB_ERR_INVALID, "locator detection");
+      if (L.location < DFB_LOCATE_STEP_BEGIN || L.location > DFB_LOCATE_REGULA_FALSI)
+        return fail(DFB_ERR_INVALID, "locator location");
+      if (L.detection != DFB_DET_STEP && (L.detector_id < 1 || L.detector_id > info->n_detectors))
+        return fail(DFB_ERR_INVALID, "detector_id not registered for this system");
+    }
+    if (L.kind == DFB_LOC_PROPAGATION && (L.detector_id < 0 || L.detector_id > info->n_detectors))
+      return fail(DFB_ERR_INVALID, "delayed-argument id not registered for this system");
+    if (L.kind == DFB_LOC_PERIODIC && !(L.period > 0.0))
+      return fail(DFB_ERR_INVALID, "Periodic period must be > 0");
+    if (L.callback_id < 0 || L.callback_id > info->n_callbacks)
+      return fail(DFB_ERR_INVALID, "callback_id not registered for this system");
+    if (L.filter < DFB_FILTER_NONE || L.filter > DFB_FILTER_IN_INTERVAL)
+      return fail(DFB_ERR_INVALID, "locator filter");
+    if (L.filter == DFB_FILTER_EVERY && L.filter_n < 1) return fail(DFB_ERR_INVALID, "every(n): n >= 1");
+  }
+  if (p.trace_every < 0 || p.trace_capacity < 0 || p.event_capacity < 0 || p.ring_capacity < 0)
+    return fail(DFB_ERR_INVALID, "negative capacity");
+  *info_out = info;
+  return DFB_OK;
+}
+
+void sparsity(const dfb_tableau& rk, unsigned long long* amask, unsigned* bmask) {
+  unsigned long long am = 0;
+  unsigned bm = 0;
+  for (int i = 1; i < rk.S; ++i)
+    for (int j = 0; j < i; ++j)
+      if (rk.a[i * DFB_MAX_STAGES + j] != 0.0) am |= 1ull << (i * 8 + j);
+  for (int j = 0; j < rk.S; ++j)
+    if (rk.b[j] != 0.0) bm |= 1u << j;
+  *amask = am;
+  *bmask = bm;
+}
+
+int launch_general(dfb_handle* h, const DevProblem& P, cudaStream_t stream) {
+  LaunchCfg cfg;
+  cfg.stream = stream;
+  cfg.block = 128;
+  cfg.grid = int((h->n + cfg.block - 1) / cfg.block);
+  const bool has_loc = P.n_loc > 0;
+  const bool fast = h->prob.arith == DFB_ARITH_FAST;
+  typedef int (*Fn)(const DevProblem&, int, bool, const LaunchCfg&, int);
+  const Fn strict_fns[] = {dfb_strict::launch_general_g1, dfb_strict::launch_general_g2,
+                           dfb_strict::launch_general_g3, dfb_strict::launch_general_g4,
+                           dfb_strict::launch_general_g5};
+  const Fn fast_fns[] = {dfb_fast::launch_general_g1, dfb_fast::launch_general_g2,
+                         dfb_fast::launch_general_g3, dfb_fast::launch_general_g4,
+                         dfb_fast::launch_general_g5};
+  for (int g = 0; g < 5; ++g) {
+    const int rc = (fast ? fast_fns : strict_fns)[g](P, h->prob.system_id, has_loc, cfg, h->locate_batch);
+    if (rc == -1) continue;
+    if (rc != 0)
+      return fail(DFB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(cudaError_t(rc)));
+    return DFB_OK;
+  }
+  return fail(DFB_ERR_UNSUPPORTED,
+              "no compiled kernel for this (system, tableau shape): see kernels_general.cu");
+}
+
+}  // namespace
+
+extern "C" {
+
+int dfb_abi_version(void) { return DFB_ABI_VERSION; }
+const char* dfb_last_error(void) { return g_last_error.c_str(); }
+
+int dfb_tableau_by_name(const char* name, dfb_tableau* out) {
+  if (!name || !out) return fail(DFB_ERR_INVALID, "null argument");
+  if (!dfb_host::tab_by_name(name, out)) return fail(DFB_ERR_INVALID, std::string("unknown tableau: ") + name);
+  return DFB_OK;
+}
+int dfb_tableau_generic_order_2(double c2, dfb_tableau* out) {
+  if (!out) return fail(DFB_ERR_INVALID, "null argument");
+  *out = dfb_host::tab_generic_order_2(c2);
+  return DFB_OK;
+}
+int dfb_tableau_generic_order_3(double c2, double c3, int has_b3, double b3, dfb_tableau* out) {
+  if (!out) return fail(DFB_ERR_INVALID, "null argument");
+  if (!dfb_host::tab_generic_order_3(c2, c3, has_b3 != 0, b3, out))
+    return fail(DFB_ERR_INVALID, "Provided arguments are incorrect.");  // rk.rs:200
+  return DFB_OK;
+}
+
+int dfb_problem_default(dfb_problem* p) {
+  if (!p) return fail(DFB_ERR_INVALID, "null argument");
+  std::memset(p, 0, sizeof(*p));
+  p->abi_version = DFB_ABI_VERSION;
+  p->history_id = DFB_HIST_CONSTANT;
+  p->arith = DFB_ARITH_STRICT;
+  p->rk = dfb_host::tab_rktp64();  // solver.rs:88
+  p->t0 = 0.0;
+  p->t1 = std::numeric_limits<double>::infinity();
+  p->stepsize_kind = DFB_STEP_FIXED;
+  p->h = 0.05;  // solver.rs:89
+  p->max_delay = 0.0;
+  return DFB_OK;
+}
+
+int dfb_system_info_get(int32_t system_id, dfb_system_info* out) {
+  const SysInfo* s = find_system(system_id);
+  if (!s || !out) return fail(DFB_ERR_INVALID, "unknown system_id");
+  out->n_state = s->n_state;
+  out->n_params = s->n_params;
+  out->n_aux = s->n_aux;
+  out->n_detectors = s->n_detectors;
+  out->n_callbacks = s->n_callbacks;
+  out->uses_history = s->uses_history;
+  return DFB_OK;
+}
+
+int dfb_create(const dfb_problem* desc, size_t n_traj, int device, dfb_handle** out) {
+  if (!desc || !out) return fail(DFB_ERR_INVALID, "null argument");
+  if (n_traj == 0) return fail(DFB_ERR_INVALID, "n_traj must be > 0");
+  const SysInfo* info = nullptr;
+  int rc = validate(*desc, &info);
+  if (rc != DFB_OK) return rc;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    return fail(DFB_ERR_NO_DEVICE,
+                "no CUDA device: diffurch_b200 has no CPU execution path (sm_100a kernels only)");
+  }
+  if (device < 0 || device >= n_dev) return fail(DFB_ERR_INVALID, "device index out of range");
+  DFB_CUDA(cudaSetDevice(device));
+
+  dfb_handle* h = new dfb_handle();
+  h->prob = *desc;
+  h->info = *info;
+  h->n = n_traj;
+  h->device = device;
+  if (const char* e = std::getenv("DFB_LOCATE_BATCH")) h->locate_batch = std::atoi(e) > 0 ? std::atoi(e) : 1;
+  for (int l = 0; l < desc->n_loc; ++l)
+    if (desc->loc[l].kind == DFB_LOC_PROPAGATION) h->uses_disco = true;
+  if (desc->n_disco > 0) h->uses_disco = true;
+
+  const size_t n = n_traj;
+  const int N = info->n_state, S = desc->rk.S;
+#define H_ALLOC(ptr, count)                                                                    \
+  do {                                                                                         \
+    cudaError_t _e = dalloc(&(ptr), (count));                                                  \
+    if (_e != cudaSuccess) {                                                                   \
+      free_all(h);                                                                             \
+      delete h;                                                                                \
+      return fail(DFB_ERR_CUDA, std::string("cudaMalloc " #ptr ": ") + cudaGetErrorString(_e)); \
+    }                                                                                          \
+  } while (0)
+  H_ALLOC(h->d_y0, n * N);
+  H_ALLOC(h->d_params, n * size_t(info->n_params));
+  h->stage_width = size_t(N > info->n_params ? N : info->n_params);
+  if (size_t(info->n_aux) > h->stage_width) h->stage_width = size_t(info->n_aux);
+  H_ALLOC(h->d_stage, n * h->stage_width);
+  H_ALLOC(h->d_t, n);
+  H_ALLOC(h->d_y, n * N);
+  H_ALLOC(h->d_aux, n * size_t(info->n_aux));
+  H_ALLOC(h->d_steps, n);
+  H_ALLOC(h->d_rejected, n);
+  H_ALLOC(h->d_events, n);
+  H_ALLOC(h->d_rhs, n);
+  H_ALLOC(h->d_status, n);
+  if (desc->trace_every > 0 && desc->trace_capacity > 0) {
+    H_ALLOC(h->d_trace_t, n * size_t(desc->trace_capacity));
+    H_ALLOC(h->d_trace_y, n * size_t(desc->trace_capacity) * N);
+    H_ALLOC(h->d_nsamples, n);
+  }
+  if (desc->event_capacity > 0) {
+    H_ALLOC(h->d_ev_t, n * size_t(desc->event_capacity));
+    H_ALLOC(h->d_ev_idx, n * size_t(desc->event_capacity));
+    H_ALLOC(h->d_nevents, n);
+  }
+  if (info->uses_history) {
+    size_t cap = size_t(desc->ring_capacity);
+    if (cap == 0) {
+      // window of the reference's deque: ceil(max_delay / h) + 3 records, plus two
+      // per located event inside the window (solver.rs:304,308); doubled for slack.
+      double hmin = desc->stepsize_kind == DFB_STEP_AUTOMATIC ? desc->automatic.stepsize_min : desc->h;
+      double want = std::isfinite(desc->max_delay) && hmin > 0 ? std::ceil(desc->max_delay / hmin) : 1024.0;
+      if (!(want < 1e6)) want = 1e6;
+      cap = size_t(want) * 2 + 16;
+    }
+    cap = next_pow2(cap);
+    if (cap > (1u << 20)) {
+      free_all(h);
+      delete h;
+      return fail(DFB_ERR_INVALID, "history ring capacity too large; set ring_capacity explicitly");
+    }
+    h->ring_capacity = int(cap);
+    H_ALLOC(h->d_ring_t, n * cap);
+    H_ALLOC(h->d_ring_y, n * cap * N);
+    H_ALLOC(h->d_ring_k, n * cap * N * S);
+  }
+  if (h->uses_disco) {
+    H_ALLOC(h->d_disco_t, n * DFB_DISCO_CAP);
+    H_ALLOC(h->d_disco_ord, n * DFB_DISCO_CAP);
+  }
+#undef H_ALLOC
+  cudaEventCreate(&h->ev0);
+  cudaEventCreate(&h->ev1);
+  if (info->n_params == 0) h->has_params = true;
+  *out = h;
+  return DFB_OK;
+}
+
+void dfb_destroy(dfb_handle* h) {
+  if (!h) return;
+  free_all(h);
+  delete h;
+}
+
+static int upload_aos(dfb_handle* h, const double* host, double* dst, int width) {
+  if (width == 0) return DFB_OK;
+  DFB_CUDA(cudaSetDevice(h->device));
+  const size_t n = h->n;
+  DFB_CUDA(cudaMemcpyAsync(h->d_stage, host, n * width * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const int block = 256;
+  aos_to_soa_kernel<<<unsigned((n + block - 1) / block), block, 0, h->stream>>>(h->d_stage, dst, n, width);
+  DFB_CUDA(cudaGetLastError());
+  // the staging buffer is reused by the next upload; the caller's buffer may be freed
+  DFB_CUDA(cudaStreamSynchronize(h->stream));
+  return DFB_OK;
+}
+
+int dfb_set_initial(dfb_handle* h, const double* y0) {
+  if (!h || !y0) return fail(DFB_ERR_INVALID, "null argument");
+  int rc = upload_aos(h, y0, h->d_y0, h->info.n_state);
+  if (rc != DFB_OK) return rc;
+  h->d_y0_ext = nullptr;
+  h->has_initial = true;
+  return DFB_OK;
+}
+int dfb_set_params(dfb_handle* h, const double* params) {
+  if (!h) return fail(DFB_ERR_INVALID, "null argument");
+  if (h->info.n_params == 0) return DFB_OK;
+  if (!params) return fail(DFB_ERR_INVALID, "null argument");
+  int rc = upload_aos(h, params, h->d_params, h->info.n_params);
+  if (rc != DFB_OK) return rc;
+  h->d_params_ext = nullptr;
+  h->has_params = true;
+  return DFB_OK;
+}
+int dfb_set_initial_device(dfb_handle* h, const double* d_y0) {
+  if (!h || !d_y0) return fail(DFB_ERR_INVALID, "null argument");
+  h->d_y0_ext = d_y0;
+  h->has_initial = true;
+  return DFB_OK;
+}
+int dfb_set_params_device(dfb_handle* h, const double* d_params) {
+  if (!h || !d_params) return fail(DFB_ERR_INVALID, "null argument");
+  h->d_params_ext = d_params;
+  h->has_params = true;
+  return DFB_OK;
+}
+
+int dfb_run(dfb_handle* h, void* stream_v) {
+  if (!h) return fail(DFB_ERR_INVALID, "null handle");
+  if (!h->has_initial) return fail(DFB_ERR_STATE, "dfb_set_initial not called");
+  if (!h->has_params) return fail(DFB_ERR_STATE, "dfb_set_params not called");
+  DFB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  h->stream = stream;
+  const dfb_problem& p = h->prob;
+  const size_t n = h->n;
+  const double* y0 = h->d_y0_ext ? h->d_y0_ext : h->d_y0;
+  const double* params = h->d_params_ext ? h->d_params_ext : h->d_params;
+  h->launches = 0;
+
+  // Hot path: fixed step, no locators, no history, final state only.
+  const bool hot_eligible = p.stepsize_kind == DFB_STEP_FIXED && p.n_loc == 0 &&
+                            !h->info.uses_history && p.trace_every == 0 && p.max_steps == 0 &&
+                            p.history_id == DFB_HIST_CONSTANT && !std::getenv("DFB_FORCE_GENERAL");
+  h->used_hot_path = false;
+  if (hot_eligible) {
+    DFB_CUDA(cudaMemsetAsync(h->d_rejected, 0, n * sizeof(unsigned long long), stream));
+    DFB_CUDA(cudaMemsetAsync(h->d_events, 0, n * sizeof(unsigned long long), stream));
+    if (h->info.n_aux) DFB_CUDA(cudaMemsetAsync(h->d_aux, 0, n * h->info.n_aux * sizeof(double), stream));
+    DFB_CUDA(cudaEventRecord(h->ev0, stream));
+    auto shim = p.arith == DFB_ARITH_FAST ? dfb_fast::run_ode_fixed_shim : dfb_strict::run_ode_fixed_shim;
+    const int rc = shim(p.system_id, p.rk, p.t0, p.t1, p.h, n, y0, params, h->d_t, h->d_y,
+                        h->d_steps, h->d_rhs, h->d_status, stream);
+    if (rc > 0) return fail(DFB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(cudaError_t(rc)));
+    if (rc == 0) {
+      DFB_CUDA(cudaEventRecord(h->ev1, stream));
+      h->launches = 1;
+      h->used_hot_path = true;
+      h->ran = true;
+      return DFB_OK;
+    }
+    // rc == -1: no specialised kernel -> general path below
+  }
+
+  DevProblem P;
+  std::memset(&P, 0, sizeof(P));
+  P.rk = p.rk;
+  for (int l = 0; l < DFB_MAX_LOCATORS; ++l) P.loc[l] = p.loc[l];
+  P.automatic = p.automatic;
+  P.t0 = p.t0;
+  P.t1 = p.t1;
+  P.h = p.h;
+  P.max_delay = p.max_delay;
+  for (int i = 0; i < DFB_MAX_DISCO; ++i) {
+    P.disco_t[i] = p.disco_t[i];
+    P.disco_order[i] = p.disco_order[i];
+  }
+  P.n_disco = p.n_disco;
+  P.n_loc = p.n_loc;
+  P.history_id = p.history_id;
+  P.stepsize_kind = p.stepsize_kind;
+  P.trace_every = h->d_trace_t ? p.trace_every : 0;
+  P.trace_capacity = p.trace_capacity;
+  P.event_capacity = h->d_ev_t ? p.event_capacity : 0;
+  P.ring_capacity = h->ring_capacity;
+  P.uses_disco = h->uses_disco ? 1 : 0;
+  P.max_steps = p.max_steps;
+  P.n_traj = n;
+  P.y0 = y0;
+  P.params = params;
+  P.t_final = h->d_t;
+  P.y_final = h->d_y;
+  P.aux_final = h->info.n_aux ? h->d_aux : nullptr;
+  P.steps = h->d_steps;
+  P.rejected = h->d_rejected;
+  P.events = h->d_events;
+  P.rhs_evals = h->d_rhs;
+  P.status = h->d_status;
+  P.trace_t = h->d_trace_t;
+  P.trace_y = h->d_trace_y;
+  P.n_samples = h->d_nsamples;
+  P.ev_t = h->d_ev_t;
+  P.ev_idx = h->d_ev_idx;
+  P.n_events = h->d_nevents;
+  P.ring_t = h->d_ring_t;
+  P.ring_y = h->d_ring_y;
+  P.ring_k = h->d_ring_k;
+  P.disco_buf_t = h->d_disco_t;
+  P.disco_buf_ord = h->d_disco_ord;
+  DFB_CUDA(cudaEventRecord(h->ev0, stream));
+  int rc = launch_general(h, P, stream);
+  if (rc != DFB_OK) return rc;
+  DFB_CUDA(cudaEventRecord(h->ev1, stream));
+  h->launches = 1;
+  h->ran = true;
+  return DFB_OK;
+}
+
+int dfb_synchronize(dfb_handle* h) {
+  if (!h) return fail(DFB_ERR_INVALID, "null handle");
+  DFB_CUDA(cudaSetDevice(h->device));
+  DFB_CUDA(cudaStreamSynchronize(h->stream));
+  return DFB_OK;
+}
+
+static int download_aos(dfb_handle* h, const double* d_soa, double* host, int width) {
+  const size_t n = h->n;
+  if (width == 1) {
+    DFB_CUDA(cudaMemcpyAsync(host, d_soa, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    DFB_CUDA(cudaStreamSynchronize(h->stream));
+    return DFB_OK;
+  }
+  const int block = 256;
+  soa_to_aos_kernel<<<unsigned((n + block - 1) / block), block, 0, h->stream>>>(d_soa, h->d_stage, n, width);
+  DFB_CUDA(cudaGetLastError());
+  DFB_CUDA(cudaMemcpyAsync(host, h->d_stage, n * width * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA(cudaStreamSynchronize(h->stream));
+  return DFB_OK;
+}
+
+int dfb_get_final(dfb_handle* h, double* t, double* y, double* aux) {
+  if (!h) return fail(DFB_ERR_INVALID, "null handle");
+  if (!h->ran) return fail(DFB_ERR_STATE, "dfb_run not called");
+  DFB_CUDA(cudaSetDevice(h->device));
+  int rc;
+  if (t && (rc = download_aos(h, h->d_t, t, 1)) != DFB_OK) return rc;
+  if (y && (rc = download_aos(h, h->d_y, y, h->info.n_state)) != DFB_OK) return rc;
+  if (aux && h->info.n_aux && (rc = download_aos(h, h->d_aux, aux, h->info.n_aux)) != DFB_OK) return rc;
+  return DFB_OK;
+}
+
+int dfb_get_stats(dfb_handle* h, dfb_stats* out) {
+  if (!h || !out) return fail(DFB_ERR_INVALID, "null argument");
+  if (!h->ran) return fail(DFB_ERR_STATE, "dfb_run not called");
+  DFB_CUDA(cudaSetDevice(h->device));
+  DFB_CUDA(cudaStreamSynchronize(h->stream));
+  const size_t n = h->n;
+  if (out->steps) DFB_CUDA(cudaMemcpy(out->steps, h->d_steps, n * 8, cudaMemcpyDeviceToHost));
+  if (out->rejected) DFB_CUDA(cudaMemcpy(out->rejected, h->d_rejected, n * 8, cudaMemcpyDeviceToHost));
+  if (out->events) DFB_CUDA(cudaMemcpy(out->events, h->d_events, n * 8, cudaMemcpyDeviceToHost));
+  if (out->rhs_evals) DFB_CUDA(cudaMemcpy(out->rhs_evals, h->d_rhs, n * 8, cudaMemcpyDeviceToHost));
+  if (out->status) DFB_CUDA(cudaMemcpy(out->status, h->d_status, n * 4, cudaMemcpyDeviceToHost));
+  return DFB_OK;
+}
+
+int dfb_get_totals(dfb_handle* h, dfb_totals* out) {
+  if (!h || !out) return fail(DFB_ERR_INVALID, "null argument");
+  if (!h->ran) return fail(DFB_ERR_STATE, "dfb_run not called");
+  DFB_CUDA(cudaSetDevice(h->device));
+  DFB_CUDA(cudaStreamSynchronize(h->stream));
+  const size_t n = h->n;
+  std::vector<unsigned long long> a(n), b(n), c(n), d(n);
+  std::vector<uint32_t> st(n);
+  DFB_CUDA(cudaMemcpy(a.data(), h->d_steps, n * 8, cudaMemcpyDeviceToHost));
+  DFB_CUDA(cudaMemcpy(b.data(), h->d_rejected, n * 8, cudaMemcpyDeviceToHost));
+  DFB_CUDA(cudaMemcpy(c.data(), h->d_events, n * 8, cudaMemcpyDeviceToHost));
+  DFB_CUDA(cudaMemcpy(d.data(), h->d_rhs, n * 8, cudaMemcpyDeviceToHost));
+  DFB_CUDA(cudaMemcpy(st.data(), h->d_status, n * 4, cudaMemcpyDeviceToHost));
+  std::memset(out, 0, sizeof(*out));
+  out->n_traj = n;
+  for (size_t i = 0; i < n; ++i) {
+    out->steps += a[i];
+    out->rejected += b[i];
+    out->events += c[i];
+    out->rhs_evals += d[i];
+    if (st[i] & ~uint32_t(DFB_TRAJ_STOPPED)) out->n_failed++;
+  }
+  float ms = 0.f;
+  DFB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  out->kernel_ms = ms;
+  out->kernel_launches = h->launches;
+  return DFB_OK;
+}
+
+int dfb_final_device(dfb_handle* h, const double** d_t, const double** d_y, const double** d_aux) {
+  if (!h) return fail(DFB_ERR_INVALID, "null handle");
+  if (!h->ran) return fail(DFB_ERR_STATE, "dfb_run not called");
+  if (d_t) *d_t = h->d_t;
+  if (d_y) *d_y = h->d_y;
+  if (d_aux) *d_aux = h->info.n_aux ? h->d_aux : nullptr;
+  return DFB_OK;
+}
+
+int dfb_get_trace(dfb_handle* h, uint32_t* n_samples, double* t, double* y) {
+  if (!h) return fail(DFB_ERR_INVALID, "null handle");
+  if (!h->ran) return fail(DFB_ERR_STATE, "dfb_run not called");
+  if (!h->d_trace_t) return fail(DFB_ERR_STATE, "problem was created without a trace (trace_every/trace_capacity)");
+  DFB_CUDA(cudaSetDevice(h->device));
+  DFB_CUDA(cudaStreamSynchronize(h->stream));
+  const size_t n = h->n, cap = size_t(h->prob.trace_capacity);
+  const int N = h->info.n_state;
+  std::vector<uint32_t> ns(n);
+  DFB_CUDA(cudaMemcpy(ns.data(), h->d_nsamples, n * 4, cudaMemcpyDeviceToHost));
+  if (n_samples) std::memcpy(n_samples, ns.data(), n * 4);
+  // device layout [cap][n] / [cap][N][n] -> host [n][cap] / [n][cap][N]
+  if (t) {
+    std::vector<double> tmp(n * cap);
+    DFB_CUDA(cudaMemcpy(tmp.data(), h->d_trace_t, n * cap * 8, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i)
+      for (size_t s = 0; s < cap; ++s) t[i * cap + s] = s < ns[i] ? tmp[s * n + i] : 0.0;
+  }
+  if (y) {
+    std::vector<double> tmp(n * cap * N);
+    DFB_CUDA(cudaMemcpy(tmp.data(), h->d_trace_y, n * cap * N * 8, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i)
+      for (size_t s = 0; s < cap; ++s)
+        for (int c = 0; c < N; ++c)
+          y[(i * cap + s) * N + c] = s < ns[i] ? tmp[(s * N + c) * n + i] : 0.0;
+  }
+  return DFB_OK;
+}
+
+int dfb_get_events(dfb_handle* h, uint32_t* n_events, double* t, int32_t* index) {
+  if (!h) return fail(DFB_ERR_INVALID, "null handle");
+  if (!h->ran) return fail(DFB_ERR_STATE, "dfb_run not called");
+  if (!h->d_ev_t) return fail(DFB_ERR_STATE, "problem was created without an event log (event_capacity)");
+  DFB_CUDA(cudaSetDevice(h->device));
+  DFB_CUDA(cudaStreamSynchronize(h->stream));
+  const size_t n = h->n, cap = size_t(h->prob.event_capacity);
+  std::vector<uint32_t> ne(n);
+  DFB_CUDA(cudaMemcpy(ne.data(), h->d_nevents, n * 4, cudaMemcpyDeviceToHost));
+  if (n_events) std::memcpy(n_events, ne.data(), n * 4);
+  if (t) {
+    std::vector<double> tmp(n * cap);
+    DFB_CUDA(cudaMemcpy(tmp.data(), h->d_ev_t, n * cap * 8, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i)
+      for (size_t s = 0; s < cap; ++s) t[i * cap + s] = s < ne[i] ? tmp[s * n + i] : 0.0;
+  }
+  if (index) {
+    std::vector<int32_t> tmp(n * cap);
+    DFB_CUDA(cudaMemcpy(tmp.data(), h->d_ev_idx, n * cap * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i)
+      for (size_t s = 0; s < cap; ++s) index[i * cap + s] = s < ne[i] ? tmp[s * n + i] : -1;
+  }
+  return DFB_OK;
+}
+
+// ncclAllGather of the packed final state over NVLink.  NCCL is resolved at
+// run time from the process (the caller created the communicator with its own
+// NCCL), so this library does not link a second copy.
+int dfb_gather_final(dfb_handle* h, void* nccl_comm, int n_ranks, double* t_all, double* y_all,
+                     double* aux_all) {
+  if (!h || !nccl_comm || n_ranks < 1) return fail(DFB_ERR_INVALID, "null argument");
+  if (!h->ran) return fail(DFB_ERR_STATE, "dfb_run not called");
+  typedef int (*AllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
+  AllGatherFn all_gather = reinterpret_cast<AllGatherFn>(dlsym(RTLD_DEFAULT, "ncclAllGather"));
+  if (!all_gather) {
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (lib) all_gather = reinterpret_cast<AllGatherFn>(dlsym(lib, "ncclAllGather"));
+  }
+  if (!all_gather) return fail(DFB_ERR_NCCL, "ncclAllGather not found in the process");
+  DFB_CUDA(cudaSetDevice(h->device));
+  const size_t n = h->n;
+  const int N = h->info.n_state, A = h->info.n_aux;
+  const size_t width = size_t(1 + N + A);
+  // pack [t | y (SoA) | aux (SoA)] contiguously, gather, unpack on the host
+  double *d_pack = nullptr, *d_all = nullptr;
+  DFB_CUDA(cudaMalloc(&d_pack, n * width * 8));
+  DFB_CUDA(cudaMalloc(&d_all, n * width * 8 * size_t(n_ranks)));
+  DFB_CUDA(cudaMemcpyAsync(d_pack, h->d_t, n * 8, cudaMemcpyDeviceToDevice, h->stream));
+  DFB_CUDA(cudaMemcpyAsync(d_pack + n, h->d_y, n * N * 8, cudaMemcpyDeviceToDevice, h->stream));
+  if (A) DFB_CUDA(cudaMemcpyAsync(d_pack + n * (1 + N), h->d_aux, n * A * 8, cudaMemcpyDeviceToDevice, h->stream));
+  const int nccl_double = 8;  // ncclFloat64
+  const int nrc = all_gather(d_pack, d_all, n * width, nccl_double, nccl_comm, h->stream);
+  if (nrc != 0) {
+    cudaFree(d_pack);
+    cudaFree(d_all);
+    return fail(DFB_ERR_NCCL, "ncclAllGather failed with code " + std::to_string(nrc));
+  }
+  std::vector<double> host(n * width * size_t(n_ranks));
+  DFB_CUDA(cudaMemcpyAsync(host.data(), d_all, host.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(d_pack);
+  cudaFree(d_all);
+  for (int r = 0; r < n_ranks; ++r) {
+    const double* base = host.data() + size_t(r) * n * width;
+    for (size_t i = 0; i < n; ++i) {
+      const size_t g = size_t(r) * n + i;
+      if (t_all) t_all[g] = base[i];
+      if (y_all)
+        for (int c = 0; c < N; ++c) y_all[g * N + c] = base[n * (1 + c) + i];
+      if (aux_all)
+        for (int c = 0; c < A; ++c) aux_all[g * A + c] = base[n * (1 + N + c) + i];
+    }
+  }
+  return DFB_OK;
+}
+
+int dfb_measure_fp64_peak(int device, double* tflops, double* sm_mhz_est) {
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    return fail(DFB_ERR_NO_DEVICE, "no CUDA device");
+  }
+  DFB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  DFB_CUDA(cudaGetDeviceProperties(&prop, device));
+  const int block = 256, blocks = prop.multiProcessorCount * 8;
+  const int iters = 4096;
+  double* d_out = nullptr;
+  long long* d_cyc = nullptr;
+  DFB_CUDA(cudaMalloc(&d_out, size_t(block) * blocks * 8));
+  DFB_CUDA(cudaMalloc(&d_cyc, 8));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0);
+    dfma_chain_kernel<<<blocks, block>>>(d_out, iters, 0.999999, 1e-7, d_cyc);
+    cudaEventRecord(e1);
+    DFB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep >= 2 && ms < best) best = ms;
+  }
+  long long cyc = 0;
+  DFB_CUDA(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost));
+  const double flops = 2.0 * 64.0 * double(iters) * double(block) * double(blocks);
+  if (tflops) *tflops = flops / (double(best) * 1e-3) / 1e12;
+  if (sm_mhz_est) *sm_mhz_est = double(cyc) / (double(best) * 1e-3) / 1e6;
+  cudaFree(d_out);
+  cudaFree(d_cyc);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return DFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,775 @@
+// General per-trajectory integrator: the device form of the reference's
+// `Solver::run` (src/solver.rs:263-314) with every builder feature selectable at
+// run time from the DevProblem block: fixed or automatic stepsize, up to MAXL
+// locators of any detection/location kind, Periodic, discontinuity propagation,
+// delay history.  One trajectory per thread; State (state.rs:26-42) in
+// registers; the history ring in HBM as structure-of-arrays.
+//
+// The loop is written as a state machine with ONE make_step call site, so the
+// lanes of a warp that re-take a step (rejected step, step truncated to an
+// event time) run their stages together with the lanes that take an ordinary
+// step.  Event location (bisection) is deferred: a lane that detects an event
+// parks until enough lanes of its warp are parked (or nobody else can advance),
+// then the parked lanes run their bisections together (warp-level batching).
+#pragma once
+#include "common.cuh"
+#include "systems.cuh"
+
+namespace DFB_NS {
+
+__device__ __forceinline__ double dev_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+__device__ __forceinline__ double dev_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// f64::powi (compiler-rt __powidf2 / LLVM ExpandPowI): square-and-multiply.
+__device__ __forceinline__ double dev_powi(double a, int b) {
+  double r = 1.0;
+  const bool recip = b < 0;
+  while (true) {
+    if (b & 1) r *= a;
+    b /= 2;
+    if (b == 0) break;
+    a *= a;
+  }
+  return recip ? 1.0 / r : r;
+}
+
+// Tableau accessor over the kernel parameter block, compile-time shape.
+template <int S_, int I_>
+struct ParamTab {
+  static constexpr int S = S_, I = I_;
+  const dfb_tableau& t;
+  __device__ __forceinline__ double a(int i, int j) const { return t.a[i * DFB_MAX_STAGES + j]; }
+  __device__ __forceinline__ double b(int j) const { return t.b[j]; }
+  __device__ __forceinline__ double b2(int j) const { return t.b2[j]; }
+  __device__ __forceinline__ double c(int j) const { return t.c[j]; }
+  __device__ __forceinline__ double bi(int i, int j) const { return t.bi[i * DFB_MAX_INTERP + j]; }
+};
+
+// ButcherTableu::dense_output::<D> (rk.rs:17-52), reference operation order.
+template <int D, int N, class Tab>
+__device__ __forceinline__ void dense_output(const Tab& tab, const double* y_prev, double t_step,
+                                             double theta, const double (*k)[N], double* out) {
+  constexpr int S = Tab::S, I = Tab::I;
+  double pw[I];  // theta^j by powi's multiply sequence
+  pw[0] = 1.0;
+  if (I > 1) pw[1] = theta;
+  if (I > 2) pw[2] = theta * theta;
+  if (I > 3) pw[3] = theta * pw[2];
+  if (I > 4) pw[4] = pw[2] * pw[2];
+  double delta[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) delta[n] = 0.0;
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+    double b_i = 0.0;
+    if (D == 0) {
+#pragma unroll
+      for (int j = 0; j < I; ++j) b_i += tab.bi(i, j) * pw[j];
+    } else {
+#pragma unroll
+      for (int j = 1; j < I; ++j) b_i += tab.bi(i, j) * pw[j - 1] * double(j);
+    }
+#pragma unroll
+    for (int n = 0; n < N; ++n) delta[n] += k[i][n] * b_i;
+  }
+  if (D == 0) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) out[n] = y_prev[n] + delta[n] * t_step;
+  } else {
+#pragma unroll
+    for (int n = 0; n < N; ++n) out[n] = delta[n];
+  }
+}
+
+// StateHistory (state.rs:11-23, 161-187) over a per-trajectory ring in HBM.
+// Ring record r holds (t_r, y_r) and the stages k of the step that ENDED at
+// t_r, i.e. k_deque[r-1] of the reference.
+template <int N, class Tab, bool ENABLED>
+struct History {
+  static constexpr int S = Tab::S;
+  const DevProblem* P;
+  Tab tab;
+  size_t gid;
+  int head, len;
+  uint32_t status;
+  double y0[N];
+  double hist_k;  // parameter of the sin history functions
+
+  __device__ __forceinline__ size_t slot(int r) const {
+    return size_t((head + r) & (P->ring_capacity - 1));
+  }
+  __device__ __forceinline__ double T(int r) const { return P->ring_t[slot(r) * P->n_traj + gid]; }
+
+  // InitialCondition::eval::<D> (initial_condition.rs:15-50)
+  template <int D>
+  __device__ void init_eval(double t, double* out) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) out[n] = 0.0;
+    switch (P->history_id) {
+      case DFB_HIST_CONSTANT:
+        if (D == 0) {
+#pragma unroll
+          for (int n = 0; n < N; ++n) out[n] = y0[n];
+        }
+        break;
+      case DFB_HIST_SIN:
+        out[0] = D == 0 ? sin(hist_k * t) : hist_k * cos(hist_k * t);
+        break;
+      case DFB_HIST_SIN_NODERIV:
+        if (D == 0) out[0] = sin(hist_k * t);
+        else {
+          status |= DFB_TRAJ_NO_DERIVATIVE;
+          out[0] = dev_nan();
+        }
+        break;
+      case DFB_HIST_INV_SQUARE:
+        if (D == 0) out[0] = 1.0 / (t * t);
+        else {
+          status |= DFB_TRAJ_NO_DERIVATIVE;
+          out[0] = dev_nan();
+        }
+        break;
+    }
+  }
+
+  template <int D>
+  __device__ void eval(double t, double* out) {
+    if (t <= P->t0) {
+      init_eval<D>(t, out);
+      return;
+    }
+    if (!ENABLED) {  // ODE systems never look anything up
+#pragma unroll
+      for (int n = 0; n < N; ++n) out[n] = dev_nan();
+      status |= DFB_TRAJ_HISTORY_NOT_READY;
+      return;
+    }
+    // VecDeque::partition_point(|t_i| t_i <= t)
+    int lo = 0, hi = len;
+    while (lo < hi) {
+      const int mid = lo + (hi - lo) / 2;
+      if (T(mid) <= t) lo = mid + 1;
+      else hi = mid;
+    }
+    if (lo == 0 || lo == len) {
+      status |= (lo == 0) ? DFB_TRAJ_HISTORY_DELETED : DFB_TRAJ_HISTORY_NOT_READY;
+#pragma unroll
+      for (int n = 0; n < N; ++n) out[n] = dev_nan();
+      return;
+    }
+    const size_t n_traj = P->n_traj;
+    const size_t s0 = slot(lo - 1), s1 = slot(lo);
+    const double t_prev = P->ring_t[s0 * n_traj + gid];
+    const double t_next = P->ring_t[s1 * n_traj + gid];
+    double y_prev[N];
+    double k[S][N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) y_prev[n] = P->ring_y[(s0 * N + n) * n_traj + gid];
+#pragma unroll
+    for (int i = 0; i < S; ++i)
+#pragma unroll
+      for (int n = 0; n < N; ++n) k[i][n] = P->ring_k[((s1 * S + i) * N + n) * n_traj + gid];
+    const double t_step = t_next - t_prev;
+    const double theta = (t - t_prev) / t_step;
+    dense_output<D, N>(tab, y_prev, t_step, theta, k, out);
+  }
+
+  // push of commit_step (state.rs:123-125)
+  __device__ void push(double t, const double* y, const double (*k)[N]) {
+    if (!ENABLED) return;
+    if (len == P->ring_capacity) {  // library limit, not a reference behaviour
+      head = (head + 1) & (P->ring_capacity - 1);
+      --len;
+      status |= DFB_TRAJ_RING_OVERFLOW;
+    }
+    const size_t n_traj = P->n_traj;
+    const size_t s = slot(len);
+    P->ring_t[s * n_traj + gid] = t;
+#pragma unroll
+    for (int n = 0; n < N; ++n) P->ring_y[(s * N + n) * n_traj + gid] = y[n];
+    if (k) {
+#pragma unroll
+      for (int i = 0; i < S; ++i)
+#pragma unroll
+        for (int n = 0; n < N; ++n) P->ring_k[((s * S + i) * N + n) * n_traj + gid] = k[i][n];
+    }
+    ++len;
+  }
+  // prune of commit_step (state.rs:126-133)
+  __device__ void prune(double t_tail) {
+    if (!ENABLED) return;
+    while (len > 1 && T(1) < t_tail) {
+      head = (head + 1) & (P->ring_capacity - 1);
+      --len;
+    }
+  }
+};
+
+// Per-trajectory discontinuity list (state.rs:20, 134-138) in HBM.
+struct DiscoList {
+  const DevProblem* P;
+  size_t gid;
+  int head, len;
+  __device__ __forceinline__ size_t slot(int r) const {
+    return size_t((head + r) & (DFB_DISCO_CAP - 1)) * P->n_traj + gid;
+  }
+  __device__ double t(int r) const { return P->disco_buf_t[slot(r)]; }
+  __device__ int order(int r) const { return P->disco_buf_ord[slot(r)]; }
+  __device__ bool push(double tt, int ord) {
+    if (len == DFB_DISCO_CAP) return false;
+    const size_t s = slot(len);
+    P->disco_buf_t[s] = tt;
+    P->disco_buf_ord[s] = ord;
+    ++len;
+    return true;
+  }
+  __device__ void prune(double t_tail) {
+    while (len > 0 && t(0) < t_tail) {
+      head = (head + 1) & (DFB_DISCO_CAP - 1);
+      --len;
+    }
+  }
+  // util::partition_point_linear (src/util/partition_point.rs:26-52), pred = t_i <= x
+  __device__ int partition_point_linear(int start, double x) const {
+    if (len == 0) return 0;
+    int i = start < len - 1 ? start : len - 1;
+    if (t(i) <= x) {
+      i += 1;
+      while (i < len && t(i) <= x) i += 1;
+    } else {
+      while (i > 0 && !(t(i - 1) <= x)) i -= 1;
+    }
+    return i;
+  }
+};
+
+enum : int { MODE_STEP = 0, MODE_EVENT_RESTEP = 1, MODE_LOCATE = 2, MODE_DONE = 3 };
+
+template <class Sys, int S, int I, bool HAS_LOC>
+struct Integrator {
+  static constexpr int N = Sys::N;
+  static constexpr int NP = Sys::NP > 0 ? Sys::NP : 1;
+  static constexpr int NA = Sys::NA > 0 ? Sys::NA : 1;
+  static constexpr int MAXL = HAS_LOC ? DFB_MAX_LOCATORS : 1;
+  using Tab = ParamTab<S, I>;
+  using Hist = History<N, Tab, Sys::uses_history>;
+  using Ref = StateRef<N, Hist>;
+  using RefMut = StateRefMut<N, Hist>;
+
+  const DevProblem& P;
+  Tab tab;
+  size_t gid;
+  // State (state.rs:26-42)
+  double t_curr, t_prev;
+  double p_curr[N], p_prev[N], d_curr[N], d_prev[N], e_curr[N];
+  double k[S][N];
+  double prm[NP];
+  double aux[NA];
+  Hist hist;
+  DiscoList disco;
+  // stepsize controller state
+  double h_auto;
+  // locator state (indexed at run time: lives in local memory, L1-resident)
+  double last_call[MAXL];
+  uint32_t has_last_call;
+  int every_i[MAXL];
+  double sep_prev[MAXL];
+  double trk_t[MAXL];
+  long long trk_order[MAXL];
+  int trk_index[MAXL];
+  // counters
+  unsigned long long n_steps, n_rejected, n_events, n_rhs;
+  uint32_t n_samples, n_evlog;
+  unsigned long long on_step_calls;
+
+  __device__ Integrator(const DevProblem& P_, size_t gid_)
+      : P(P_), tab{P_.rk}, gid(gid_), hist{&P_, Tab{P_.rk}, gid_, 0, 0, 0u, {}, 0.0},
+        disco{&P_, gid_, 0, 0} {}
+
+  // ---- views (state_fn.rs:170-201) -----------------------------------------
+  __device__ __forceinline__ Ref view_curr() { return Ref{t_curr, p_curr, d_curr, t_prev, p_prev, &hist}; }
+  __device__ __forceinline__ Ref view_prev() { return Ref{t_prev, p_prev, d_prev, t_prev, p_prev, &hist}; }
+
+  __device__ __forceinline__ void rhs_curr(double* out) {
+    Sys::rhs(view_curr(), prm, out);
+    ++n_rhs;
+  }
+
+  // State::eval::<D> (state.rs:83-92)
+  template <int D>
+  __device__ void state_eval(double t, double* out) {
+    if (t >= t_prev && t <= t_curr) {
+      const double t_step = t_curr - t_prev;
+      const double theta = (t - t_prev) / t_step;
+      dense_output<D, N>(tab, p_prev, t_step, theta, k, out);
+    } else {
+      hist.template eval<D>(t, out);
+    }
+  }
+
+  // ---- State::make_step (state.rs:94-120) ----------------------------------
+  __device__ __forceinline__ void make_step(double t_step, bool need_error) {
+    if (t_prev != t_curr) {
+#pragma unroll
+      for (int n = 0; n < N; ++n) k[0][n] = d_curr[n];
+    } else {
+      rhs_curr(k[0]);
+    }
+    t_prev = t_curr;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      p_prev[n] = p_curr[n];
+      d_prev[n] = d_curr[n];
+    }
+#pragma unroll
+    for (int i = 1; i < S; ++i) {
+      t_curr = t_prev + tab.c(i) * t_step;
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < i; ++j) acc = acc + k[j][n] * tab.a(i, j);
+        p_curr[n] = p_prev[n] + acc * t_step;
+      }
+      rhs_curr(k[i]);
+    }
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < S; ++j) acc = acc + k[j][n] * tab.b(j);
+      p_curr[n] = p_prev[n] + acc * t_step;
+    }
+    t_curr = t_prev + t_step;
+    rhs_curr(d_curr);
+    if (need_error) {
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < S; ++j) acc = acc + k[j][n] * (tab.b2(j) - tab.b(j));
+        e_curr[n] = acc * t_step;
+      }
+    }
+  }
+
+  // State::commit_step (state.rs:122-139)
+  __device__ void commit_step() {
+    hist.push(t_curr, p_curr, k);
+    const double t_tail = t_prev - P.max_delay;
+    hist.prune(t_tail);
+    if (P.uses_disco) disco.prune(t_tail);
+  }
+  __device__ __forceinline__ void make_zero_step() {  // state.rs:141-144
+    t_prev = t_curr;
+#pragma unroll
+    for (int n = 0; n < N; ++n) p_prev[n] = p_curr[n];
+  }
+  __device__ __forceinline__ void undo_step() {  // state.rs:146-150
+    t_curr = t_prev;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      p_curr[n] = p_prev[n];
+      d_curr[n] = d_prev[n];
+    }
+  }
+
+  // ---- stepsize (stepsize.rs) ----------------------------------------------
+  __device__ __forceinline__ double stepsize_get() const {
+    return P.stepsize_kind == DFB_STEP_AUTOMATIC ? h_auto : P.h;
+  }
+  // AutomaticStepsize::update (stepsize.rs:64-85); true = Rejected
+  __device__ bool stepsize_update_rejects() {
+    const dfb_auto_stepsize& A = P.automatic;
+    double err = 0.0;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      const double ae = fabs(e_curr[n]);
+      const double e = ae / (A.atol[n] + ae * A.rtol[n]);
+      err = n == 0 ? e : fmax(err, e);
+    }
+    double factor = A.fac * pow(1.0 / err, 1.0 / double(A.order + 1u));
+    factor = dev_clamp(factor, A.fac_min, A.fac_max);
+    h_auto *= factor;
+    h_auto = dev_clamp(h_auto, A.stepsize_min, A.stepsize_max);
+    return err >= 1.0;
+  }
+
+  // ---- EvalState over a locator's scalar function ---------------------------
+  // which: 0 = eval_curr, 1 = eval_prev, 2 = eval_at(t)  (state_fn.rs:170-201)
+  __device__ double loc_fn(int l, int which, double t) {
+    const dfb_locator& L = P.loc[l];
+    double y[N], dy[N];
+    Ref v = which == 1 ? view_prev() : view_curr();
+    if (which == 2) {
+      state_eval<0>(t, y);
+      state_eval<1>(t, dy);
+      v = Ref{t, y, dy, t, y, &hist};
+    }
+    if (L.kind == DFB_LOC_PROPAGATION) {
+      // Propagator as EvalState (loc.rs:424-432): delayed argument - tracked time
+      const double arg = L.detector_id == 0 ? v.t - L.delay : Sys::detector(L.detector_id, v, prm);
+      return arg - trk_t[l];
+    }
+    if (L.detection == DFB_DET_STEP) return 1.0;
+    return Sys::detector(L.detector_id, v, prm);
+  }
+
+  // detection_method (loc.rs:127-143), Periodic::detect (:318-322), Propagator (:378-410)
+  __device__ bool detect_base(int l) {
+    const dfb_locator& L = P.loc[l];
+    if (L.kind == DFB_LOC_PERIODIC) {
+      const double prev = floor((t_prev - L.offset) / L.period);
+      const double curr = floor((t_curr - L.offset) / L.period);
+      return prev < curr;
+    }
+    if (L.kind == DFB_LOC_PROPAGATION) {
+      const double keep = trk_t[l];
+      trk_t[l] = 0.0;  // loc_fn subtracts the tracked time; we want the raw delayed argument
+      const double prev = loc_fn(l, 1, 0.0);
+      const double curr = loc_fn(l, 0, 0.0);
+      trk_t[l] = keep;
+      const int pp = disco.partition_point_linear(trk_index[l], prev);
+      const int pc = disco.partition_point_linear(pp, curr);
+      trk_index[l] = pp < pc ? pp : pc;
+      if (pp != pc) {
+        trk_t[l] = disco.t(trk_index[l]);
+        trk_order[l] = (long long)disco.order(trk_index[l]) + L.smoothing_order;
+        return true;
+      }
+      return false;
+    }
+    const int det = L.detection;
+    if (det == DFB_DET_STEP) return true;
+    const bool needs_prev = det == DFB_DET_ZERO || det == DFB_DET_ABOVE_ZERO ||
+                            det == DFB_DET_BELOW_ZERO || det == DFB_DET_SWITCH ||
+                            det == DFB_DET_SWITCH_TRUE || det == DFB_DET_SWITCH_FALSE;
+    const double c = loc_fn(l, 0, 0.0);
+    const double p = needs_prev ? loc_fn(l, 1, 0.0) : 0.0;
+    const bool cb = c != 0.0, pb = p != 0.0;
+    switch (det) {
+      case DFB_DET_ZERO: return (c > 0.0 && p <= 0.0) || (c <= 0.0 && p > 0.0);
+      case DFB_DET_ABOVE_ZERO: return c > 0.0 && p <= 0.0;
+      case DFB_DET_BELOW_ZERO: return c < 0.0 && p >= 0.0;
+      case DFB_DET_POSITIVE: return c >= 0.0;
+      case DFB_DET_NEGATIVE: return c <= 0.0;
+      case DFB_DET_SWITCH: return cb != pb;
+      case DFB_DET_SWITCH_TRUE: return cb && !pb;
+      case DFB_DET_SWITCH_FALSE: return !cb && pb;
+      case DFB_DET_IS_TRUE: return cb;
+      case DFB_DET_IS_FALSE: return !cb;
+    }
+    return false;
+  }
+
+  // location_method (loc.rs:200-285), Periodic::locate (:332-334)
+  __device__ double locate_base(int l) {
+    const dfb_locator& L = P.loc[l];
+    if (L.kind == DFB_LOC_PERIODIC)
+      return floor((t_curr - L.offset) / L.period) * L.period + L.offset;
+    const int location = L.kind == DFB_LOC_PROPAGATION ? int(DFB_LOCATE_BISECTION) : L.location;
+    if (location == DFB_LOCATE_STEP_BEGIN) return t_prev;
+    if (location == DFB_LOCATE_STEP_END) return t_curr;
+    if (location == DFB_LOCATE_STEP_MIDDLE) return 0.5 * (t_curr - t_prev);  // sic (loc.rs:202-204)
+    const bool is_bool = location == DFB_LOCATE_BISECTION_BOOL;
+    const double fc = is_bool ? 0.0 : loc_fn(l, 0, 0.0);
+    const double fp = (is_bool || location == DFB_LOCATE_LERP) ? loc_fn(l, 1, 0.0) : 0.0;
+    if (location == DFB_LOCATE_LERP) return (fc * t_prev - fp * t_curr) / (fc - fp);
+    double lft = t_prev, rgt = t_curr;
+    if (is_bool ? (fp != 0.0) : (fc < 0.0)) {
+      const double tmp = lft;
+      lft = rgt;
+      rgt = tmp;
+    }
+    double w = fabs(rgt - lft);
+    double w_prev = 2.0 * w;
+    if (location == DFB_LOCATE_REGULA_FALSI) {
+      while (w < w_prev) {
+        w_prev = w;
+        double fv[3];
+        double m = 0.0;
+#pragma unroll 1
+        for (int q = 0; q < 3; ++q) {
+          if (q == 2) m = (fv[1] * lft - fv[0] * rgt) / (fv[1] - fv[0]);
+          fv[q] = loc_fn(l, 2, q == 0 ? lft : (q == 1 ? rgt : m));
+        }
+        if (fv[2] < 0.0) rgt = m;
+        else lft = m;
+        w = fabs(rgt - lft);
+      }
+      return fmax(lft, rgt);
+    }
+    // Bisection (loc.rs:235-259) / BisectionBool (:210-234)
+    double m = 0.5 * (lft + rgt);
+    while (w < w_prev) {
+      w_prev = w;
+      const double f = loc_fn(l, 2, m);
+      const bool go_left = is_bool ? !(f != 0.0) : (f < 0.0);
+      if (go_left) lft = m;
+      else rgt = m;
+      m = 0.5 * (lft + rgt);
+      w = fabs(rgt - lft);
+    }
+    return fmax(lft, rgt);
+  }
+
+  // Filter state machines (loc.rs:613-688)
+  __device__ bool filter_pass(int l, double t) {
+    const dfb_locator& L = P.loc[l];
+    switch (L.filter) {
+      case DFB_FILTER_EVERY:
+        every_i[l] += 1;
+        if (every_i[l] >= L.filter_n) {
+          every_i[l] = 0;
+          return true;
+        }
+        return false;
+      case DFB_FILTER_SEPARATED_BY:
+        if (t >= sep_prev[l] + L.filter_a) {
+          sep_prev[l] = t;
+          return true;
+        }
+        return false;
+      case DFB_FILTER_IN_INTERVAL: return t >= L.filter_a && t < L.filter_b;
+    }
+    return true;
+  }
+
+  // Detect phase of one locator, with DedupLocF (loc.rs:1002-1011) and the
+  // filter wrappers (FilterAfterDetection :484-486, FilterLocated :568-576).
+  __device__ bool detect_phase(int l) {
+    const dfb_locator& L = P.loc[l];
+    if (L.dedup && ((has_last_call >> l) & 1u) && !(t_prev > last_call[l])) return false;
+    if (!detect_base(l)) return false;
+    if (L.filter == DFB_FILTER_SEPARATED_BY || L.filter == DFB_FILTER_IN_INTERVAL) {
+      // FilterLocated::detect = inner detect_and_locate + filter.eval_at(t);
+      // LocCallback then calls locate() AGAIN (loc.rs:31-33, 733-746).
+      return filter_pass(l, locate_base(l));
+    }
+    if (L.filter == DFB_FILTER_EVERY) return filter_pass(l, t_curr);
+    return true;
+  }
+
+  // callback of locator l (LocCallback / DedupLocF::eval_mut loc.rs:1023-1026,
+  // Propagation callback loc.rs:446-453)
+  __device__ void fire_callback(int l) {
+    const dfb_locator& L = P.loc[l];
+    if (L.kind == DFB_LOC_PROPAGATION) {
+      if (trk_order[l] < (long long)P.rk.order) {
+        if (!disco.push(t_curr, int(trk_order[l]))) hist.status |= DFB_TRAJ_DISCO_OVERFLOW;
+      }
+      return;
+    }
+    if (L.dedup) {
+      has_last_call |= 1u << l;
+      last_call[l] = t_curr;
+    }
+    if (L.callback_id != DFB_CB_NONE) {
+      RefMut m{&t_curr, p_curr, d_curr, t_prev, p_prev, &hist};
+      Sys::callback(L.callback_id, m, prm, aux);
+    }
+  }
+
+  // output policy standing in for on_step closures (solver.rs:290, 309)
+  __device__ void on_step() {
+    if (P.trace_every > 0) {
+      if (on_step_calls % (unsigned long long)P.trace_every == 0 &&
+          n_samples < uint32_t(P.trace_capacity)) {
+        const size_t n_traj = P.n_traj;
+        P.trace_t[size_t(n_samples) * n_traj + gid] = t_curr;
+#pragma unroll
+        for (int n = 0; n < N; ++n)
+          P.trace_y[(size_t(n_samples) * N + n) * n_traj + gid] = p_curr[n];
+        ++n_samples;
+      }
+      ++on_step_calls;
+    }
+  }
+
+  __device__ void init() {
+    const size_t n_traj = P.n_traj;
+#pragma unroll
+    for (int n = 0; n < Sys::NP; ++n) prm[n] = P.params[size_t(n) * n_traj + gid];
+#pragma unroll
+    for (int n = 0; n < NA; ++n) aux[n] = 0.0;
+#pragma unroll
+    for (int n = 0; n < N; ++n) hist.y0[n] = P.y0[size_t(n) * n_traj + gid];
+    hist.hist_k = Sys::NP >= 4 ? prm[Sys::NP >= 4 ? 3 : 0] : 0.0;
+    // State::new (state.rs:52-81)
+    t_curr = t_prev = P.t0;
+    double p0[N];
+    hist.template init_eval<0>(P.t0, p0);
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      p_curr[n] = p_prev[n] = p0[n];
+      d_curr[n] = d_prev[n] = e_curr[n] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < S; ++i)
+#pragma unroll
+      for (int n = 0; n < N; ++n) k[i][n] = 0.0;
+    hist.push(P.t0, p0, nullptr);
+    if (P.uses_disco)
+      for (int i = 0; i < P.n_disco; ++i) disco.push(P.disco_t[i], P.disco_order[i]);
+    h_auto = P.automatic.stepsize;
+    has_last_call = 0u;
+    for (int l = 0; l < MAXL; ++l) {
+      last_call[l] = 0.0;
+      every_i[l] = l < P.n_loc ? P.loc[l].filter_n - 1 : 0;
+      sep_prev[l] = -1.7976931348623157e308;  // T::min_value()
+      trk_t[l] = -1.7976931348623157e308;
+      trk_order[l] = 0x7fffffffffffffffLL;    // usize::MAX
+      trk_index[l] = 0;
+    }
+    n_steps = n_rejected = n_events = n_rhs = 0ull;
+    n_samples = n_evlog = 0u;
+    on_step_calls = 0ull;
+  }
+
+  __device__ void finish() {
+    const size_t n_traj = P.n_traj;
+    uint32_t status = hist.status;
+    if (t_curr == dev_inf()) status |= DFB_TRAJ_STOPPED;
+    bool finite = true;
+#pragma unroll
+    for (int n = 0; n < N; ++n) finite = finite && (fabs(p_curr[n]) < dev_inf());
+    if (!finite) status |= DFB_TRAJ_NONFINITE;
+    P.t_final[gid] = t_curr;
+#pragma unroll
+    for (int n = 0; n < N; ++n) P.y_final[size_t(n) * n_traj + gid] = p_curr[n];
+    if (P.aux_final) {
+#pragma unroll
+      for (int n = 0; n < Sys::NA; ++n) P.aux_final[size_t(n) * n_traj + gid] = aux[n];
+    }
+    P.steps[gid] = n_steps;
+    P.rejected[gid] = n_rejected;
+    P.events[gid] = n_events;
+    P.rhs_evals[gid] = n_rhs;
+    P.status[gid] = status;
+    if (P.n_samples) P.n_samples[gid] = n_samples;
+    if (P.n_events) P.n_events[gid] = n_evlog;
+  }
+
+  __device__ __forceinline__ int next_mode() {
+    if (P.max_steps > 0 && n_steps >= (unsigned long long)P.max_steps && t_curr < P.t1) {
+      hist.status |= DFB_TRAJ_STEP_LIMIT;
+      return MODE_DONE;
+    }
+    return (t_curr < P.t1) ? MODE_STEP : MODE_DONE;
+  }
+
+  // ---- Solver::run (solver.rs:275-313) as a warp-friendly state machine -----
+  // `valid` = this lane owns a trajectory.  All 32 lanes stay in the loop so
+  // the warp votes are full-mask.
+  __device__ void run(bool valid, int locate_batch_threshold) {
+    int mode = MODE_DONE;
+    if (valid) {
+      init();
+      on_step();  // events_on_step at t_init (solver.rs:290)
+      mode = next_mode();
+    }
+    double ev_time = 0.0;
+    int ev_index = 0;
+    uint32_t fired_mask = 0u;  // locators that detected on the parked step
+    const bool adaptive = P.stepsize_kind == DFB_STEP_AUTOMATIC;
+
+    while (true) {
+      const unsigned stepping =
+          __ballot_sync(0xffffffffu, mode == MODE_STEP || mode == MODE_EVENT_RESTEP);
+      const unsigned parked = HAS_LOC ? __ballot_sync(0xffffffffu, mode == MODE_LOCATE) : 0u;
+      if (stepping == 0u && parked == 0u) break;
+
+      // (1) batched event location for the parked lanes
+      if (HAS_LOC && parked != 0u &&
+          (stepping == 0u || __popc(parked) >= locate_batch_threshold)) {
+        if (mode == MODE_LOCATE) {
+          // HListLocateEarliest (loc.rs:821-835): strictly earliest, first index wins ties
+          bool found = false;
+          double best_t = 0.0;
+          int best_i = 0;
+#pragma unroll 1
+          for (int l = 0; l < P.n_loc; ++l) {
+            if ((fired_mask >> l) & 1u) {
+              const double tl = locate_base(l);
+              if (!found || tl < best_t) {
+                found = true;
+                best_t = tl;
+                best_i = l;
+              }
+            }
+          }
+          if (found && best_t >= t_prev) {  // solver.rs:299-300
+            undo_step();
+            ev_time = best_t;
+            ev_index = best_i;
+            mode = MODE_EVENT_RESTEP;
+          } else {
+            commit_step();
+            ++n_steps;
+            on_step();
+            mode = next_mode();
+          }
+        }
+        continue;
+      }
+
+      // (2) one make_step for every lane that can advance
+      if (mode == MODE_STEP || mode == MODE_EVENT_RESTEP) {
+        const bool restep = mode == MODE_EVENT_RESTEP;
+        const double h_req = restep ? (ev_time - t_curr) : fmin(stepsize_get(), P.t1 - t_curr);
+        make_step(h_req, adaptive);
+        if (hist.status & (DFB_TRAJ_HISTORY_DELETED | DFB_TRAJ_HISTORY_NOT_READY |
+                           DFB_TRAJ_NO_DERIVATIVE)) {
+          mode = MODE_DONE;  // the reference panics here
+        } else if (HAS_LOC && restep) {
+          // solver.rs:304-309
+          commit_step();
+          make_zero_step();
+          fire_callback(ev_index);
+          ++n_events;
+          if (P.event_capacity > 0) {
+            if (n_evlog < uint32_t(P.event_capacity)) {
+              P.ev_t[size_t(n_evlog) * P.n_traj + gid] = ev_time;
+              P.ev_idx[size_t(n_evlog) * P.n_traj + gid] = ev_index;
+            }
+            ++n_evlog;
+          }
+          commit_step();
+          ++n_steps;
+          on_step();
+          mode = next_mode();
+        } else if (adaptive && stepsize_update_rejects()) {
+          ++n_rejected;
+          undo_step();  // solver.rs:294-297
+        } else {
+          fired_mask = 0u;
+          if (HAS_LOC) {
+#pragma unroll 1
+            for (int l = 0; l < P.n_loc; ++l)
+              if (detect_phase(l)) fired_mask |= 1u << l;
+          }
+          if (fired_mask != 0u) {
+            mode = MODE_LOCATE;
+          } else {
+            commit_step();
+            ++n_steps;
+            on_step();
+            mode = next_mode();
+          }
+        }
+      }
+    }
+    if (valid) finish();
+  }
+};
+
+template <class Sys, int S, int I, bool HAS_LOC>
+__global__ void __launch_bounds__(128)
+    integrate_general_kernel(const __grid_constant__ DevProblem P, int locate_batch_threshold) {
+  const size_t gid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool valid = gid < P.n_traj;
+  Integrator<Sys, S, I, HAS_LOC> it(P, valid ? gid : 0);
+  it.run(valid, locate_batch_threshold);
+}
+
+}  // namespace DFB_NS

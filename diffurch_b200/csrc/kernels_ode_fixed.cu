@@ -1,0 +1,103 @@
+// Instantiations + launcher of the fixed-step ODE hot-path kernel.
+// Compiled twice (see dev/common.cuh): STRICT (-fmad=false) and FAST.
+#include "dev/ode_fixed.cuh"
+#include "launch.hpp"
+
+namespace DFB_NS {
+
+namespace {
+constexpr unsigned long long kMaskRk4 = amask_bit(1, 0) | amask_bit(2, 1) | amask_bit(3, 2);
+constexpr bool kPrescaled = (DFB_ARITH == 1);
+constexpr int kBlock = 128;
+
+template <class Sys, int S, unsigned long long AMASK, unsigned BMASK>
+bool try_launch(int S_rt, unsigned long long amask, unsigned bmask, const OdeFixedArgs& A,
+                cudaStream_t stream, int* rc) {
+  if (S_rt != S) return false;
+  if ((amask & ~AMASK) != 0ull || (bmask & ~BMASK) != 0u) return false;  // kernel must cover every non-zero
+  const size_t grid = (A.n_traj + kBlock - 1) / kBlock;
+  ode_fixed_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock>
+      <<<unsigned(grid), kBlock, 0, stream>>>(A);
+  *rc = int(cudaGetLastError());
+  return true;
+}
+
+// exact-sparsity variants first, then the full-lower-triangle catch-all
+template <class Sys>
+bool launch_common(int S, unsigned long long am, unsigned bm, const OdeFixedArgs& A,
+                   cudaStream_t st, int* rc) {
+  return try_launch<Sys, 7, amask_full_lower(7), 0x7Du>(S, am, bm, A, st, rc) ||  // rktp64
+         try_launch<Sys, 7, amask_full_lower(7), 0x7Fu>(S, am, bm, A, st, rc) ||
+         try_launch<Sys, 4, kMaskRk4, 0xFu>(S, am, bm, A, st, rc) ||              // rk4
+         try_launch<Sys, 4, amask_full_lower(4), 0xFu>(S, am, bm, A, st, rc);
+}
+template <class Sys>
+bool launch_all_shapes(int S, unsigned long long am, unsigned bm, const OdeFixedArgs& A,
+                       cudaStream_t st, int* rc) {
+  return launch_common<Sys>(S, am, bm, A, st, rc) ||
+         try_launch<Sys, 1, 0ull, 0x1u>(S, am, bm, A, st, rc) ||
+         try_launch<Sys, 2, amask_full_lower(2), 0x3u>(S, am, bm, A, st, rc) ||
+         try_launch<Sys, 3, amask_full_lower(3), 0x7u>(S, am, bm, A, st, rc) ||
+         try_launch<Sys, 5, amask_full_lower(5), 0x1Fu>(S, am, bm, A, st, rc);
+}
+}  // namespace
+
+// returns 0 = launched, >0 = CUDA error code, -1 = no compiled kernel for this combination
+int launch_ode_fixed(int system_id, int S, unsigned long long amask, unsigned bmask,
+                     const OdeFixedArgs& A, cudaStream_t stream) {
+  int rc = 0;
+  bool ok = false;
+  switch (system_id) {
+    case DFB_SYS_LORENZ: ok = launch_all_shapes<SysLorenz>(S, amask, bmask, A, stream, &rc); break;
+    case DFB_SYS_LINEAR1: ok = launch_all_shapes<SysLinear1>(S, amask, bmask, A, stream, &rc); break;
+    case DFB_SYS_HARMONIC: ok = launch_all_shapes<SysHarmonic>(S, amask, bmask, A, stream, &rc); break;
+    case DFB_SYS_LORENZ_VARIATIONAL:
+      ok = launch_common<SysLorenzVariational>(S, amask, bmask, A, stream, &rc);
+      break;
+    case DFB_SYS_LINEAR1_SIN: ok = launch_common<SysLinear1Sin>(S, amask, bmask, A, stream, &rc); break;
+    case DFB_SYS_LINEAR3: ok = launch_common<SysLinear3>(S, amask, bmask, A, stream, &rc); break;
+    case DFB_SYS_LINEAR3_MATRIX:
+      ok = launch_common<SysLinear3Matrix>(S, amask, bmask, A, stream, &rc);
+      break;
+    default: break;
+  }
+  return ok ? rc : -1;
+}
+
+// Host shim used by api.cu: builds the argument block (pre-scaled rows are
+// computed here with plain IEEE double multiplies) and launches.
+int run_ode_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h,
+                       size_t n, const double* y0, const double* params, double* t_final,
+                       double* y_final, unsigned long long* steps, unsigned long long* rhs_evals,
+                       uint32_t* status, cudaStream_t stream) {
+  OdeFixedArgs A;
+  unsigned long long amask = 0;
+  unsigned bmask = 0;
+  for (int i = 0; i < DFB_MAX_STAGES; ++i) {
+    for (int j = 0; j < DFB_MAX_STAGES; ++j) {
+      const double a = rk.a[i * DFB_MAX_STAGES + j];
+      A.a[i * DFB_MAX_STAGES + j] = a;
+      A.ha[i * DFB_MAX_STAGES + j] = h * a;
+      if (i < rk.S && j < i && a != 0.0) amask |= amask_bit(i, j);
+    }
+    A.b[i] = rk.b[i];
+    A.c[i] = rk.c[i];
+    A.hb[i] = h * rk.b[i];
+    A.hc[i] = rk.c[i] * h;
+    if (i < rk.S && rk.b[i] != 0.0) bmask |= 1u << i;
+  }
+  A.t0 = t0;
+  A.t1 = t1;
+  A.h = h;
+  A.n_traj = n;
+  A.y0 = y0;
+  A.params = params;
+  A.t_final = t_final;
+  A.y_final = y_final;
+  A.steps = steps;
+  A.rhs_evals = rhs_evals;
+  A.status = status;
+  return launch_ode_fixed(system_id, rk.S, amask, bmask, A, stream);
+}
+
+}  // namespace DFB_NS

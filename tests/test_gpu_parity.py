@@ -1,0 +1,429 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.
+
+STRICT arithmetic: bit-exact for every system without transcendental calls
+(integer/branch decisions, step counts, event times, final states, traces).
+FAST arithmetic (FMA, pre-scaled rows): within 1e-12 relative on non-chaotic
+horizons, as BASELINE.json's north_star states.  Systems that call sin/cos/log
+on the device (CUDA libm is within 1-2 ulp of glibc, not bit-equal) are compared
+to a tolerance written at each test.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import diffurch_b200 as d
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(oracle, make, **kw):
+    g = make(**kw).run()
+    o = oracle.run_solver(make(**kw), n_threads=8)
+    return g, o
+
+
+def assert_same_trace(g, o, exact=True, rtol=0.0, atol=0.0):
+    assert np.array_equal(g.trace_n, o.trace_n)
+    for i in range(len(g.trace_n)):
+        n = int(g.trace_n[i])
+        if exact:
+            assert np.array_equal(g.trace_t[i, :n], o.trace_t[i, :n])
+            assert np.array_equal(g.trace_p[i, :n], o.trace_p[i, :n])
+        else:
+            assert np.allclose(g.trace_t[i, :n], o.trace_t[i, :n], rtol=rtol, atol=atol)
+            assert np.allclose(g.trace_p[i, :n], o.trace_p[i, :n], rtol=rtol, atol=atol)
+
+
+def assert_same_counters(g, o):
+    assert np.array_equal(g.steps, o.steps)
+    assert np.array_equal(g.rejected, o.rejected)
+    assert np.array_equal(g.events, o.events)
+    assert np.array_equal(g.rhs_evals, o.rhs_evals)
+    assert np.array_equal(g.status, o.status)
+
+
+# ---------------------------------------------------------------- golden vectors on the GPU
+def test_gpu_delay_propagation_golden_vectors():
+    # tests/delay_propagation.rs:21-24, 45-50, 68-71, 91-93 — exact f64 equality
+    g = cases.delay_constant_1().run()
+    assert list(g.trace_t[0, :g.trace_n[0]]) == [0.0, 0.75, 1.0, 1.75, 2.0, 2.75, 3.0, 3.75, 4.0, 4.75, 5.0]
+    g = cases.delay_constant_2().run()
+    s = 7.0 / 8.0
+    assert list(g.trace_t[0, :g.trace_n[0]]) == [0.0, s, 1.0, 1.25, 2., 2.25, 2.5, 3.0, 3.25, 3.5,
+                                                  3.75, 4., 4.25, 4.5, 4.75, 5.0]
+    g = cases.delay_constant_1_smoothing().run()
+    assert list(g.trace_t[0, :g.trace_n[0]]) == [0., 0.75, 1., 1.75, 2., 2.75, 3., 3.75, 4.5, 5.25, 6.]
+    g = cases.delay_pantograph().run()
+    ts = set(g.trace_t[0, :g.trace_n[0]])
+    for i in range(1, 11):
+        assert 2.0 ** i in ts
+
+
+def test_gpu_equation_types_golden():
+    # tests/equation_types.rs:15, 38-40: exact; :77, :94, :110: reference tolerances
+    g = cases.eq_constant().run()
+    for t, p in zip(g.trace_t[0, :g.trace_n[0]], g.trace_p[0]):
+        assert list(p) == [t, -t, 0.0]
+    g = cases.eq_time().run()
+    for t, p in zip(g.trace_t[0, :g.trace_n[0]], g.trace_p[0]):
+        assert list(p) == [0.0, t, t * t / 2.0]
+    for arith in ("strict", "fast"):
+        g = cases.eq_ode_exponent().arith(arith).run()
+        n = g.trace_n[0]
+        assert np.all(np.abs(g.trace_p[0, :n, 0] - np.exp(-g.trace_t[0, :n])) < 1e-14)
+        g = cases.eq_ode_harmonic().arith(arith).run()
+        n = g.trace_n[0]
+        assert np.all(np.abs(g.trace_p[0, :n, 0] - np.sin(g.trace_t[0, :n])) < 1e-13)
+        g = cases.eq_odet_lin().arith(arith).run()
+        n = g.trace_n[0]
+        assert np.all(np.abs(g.trace_p[0, :n, 0] - g.trace_t[0, :n] ** -2.0) < 1e-13)
+
+
+# ---------------------------------------------------------------- strict = bit-exact vs the oracle
+@pytest.mark.parametrize("name", ["delay_constant_1", "delay_constant_2", "delay_constant_1_smoothing",
+                                  "delay_pantograph", "eq_constant", "eq_time", "eq_ode_exponent",
+                                  "eq_ode_harmonic", "eq_odet_lin"])
+def test_strict_bit_exact_traces(oracle, name):
+    g, o = run_both(oracle, getattr(cases, name))
+    assert_same_counters(g, o)
+    assert_same_trace(g, o, exact=True)
+    assert np.array_equal(g.t, o.t) and np.array_equal(g.p, o.p)
+
+
+@pytest.mark.parametrize("rk", ["rktp64", "rk4", "rk43", "three_eights", "euler", "midpoint", "heun2",
+                                "ralston2", "kutta3", "heun3", "ralston3", "wray3", "ssp3"])
+def test_lorenz_strict_bit_exact_all_tableaux(oracle, rk):
+    # both the hot-path kernel and the oracle, 257 trajectories (ragged last block), t in [0, 5]
+    mk = lambda: cases.lorenz(n=257, t1=5.0, rk=d.RK.by_name(rk))
+    g, o = run_both(oracle, mk)
+    assert_same_counters(g, o)
+    assert np.array_equal(g.t, o.t)
+    assert np.array_equal(g.p, o.p)
+
+
+def test_lorenz_hot_path_equals_general_path(oracle):
+    mk = lambda: cases.lorenz(n=300, t1=3.0)
+    hot = mk().run()
+    os.environ["DFB_FORCE_GENERAL"] = "1"
+    try:
+        gen = mk().run()
+    finally:
+        del os.environ["DFB_FORCE_GENERAL"]
+    assert np.array_equal(hot.p, gen.p) and np.array_equal(hot.t, gen.t)
+    assert np.array_equal(hot.steps, gen.steps) and np.array_equal(hot.rhs_evals, gen.rhs_evals)
+    # trace forces the general kernel too; its last sample is the final state
+    tr = cases.lorenz(n=300, t1=3.0, trace=d.Trace(1, 800)).run()
+    assert np.array_equal(tr.p, hot.p)
+    n = tr.trace_n[0]
+    assert n == hot.steps[0] + 1
+    assert np.array_equal(tr.trace_p[:, n - 1, :], hot.p)
+
+
+def test_lorenz_fast_within_1e12_short_horizon(oracle):
+    # north_star: fixed-step trajectories within 1e-12 relative; chaotic systems on short horizons
+    for rk in ("rktp64", "rk4"):
+        mk = lambda arith: cases.lorenz(n=512, t1=2.0, rk=d.RK.by_name(rk), arith=arith)
+        g = mk("fast").run()
+        o = oracle.run_solver(mk("strict"), n_threads=8)
+        assert np.array_equal(g.steps, o.steps)
+        rel = np.max(np.abs(g.p - o.p) / np.maximum(np.abs(o.p), 1.0))
+        assert rel < 1e-12, rel
+
+
+def test_linear_systems_fast_within_1e12(oracle):
+    # non-chaotic: harmonic oscillator and exponential decay over the reference's horizons
+    for mk in (cases.eq_ode_harmonic, cases.eq_ode_exponent):
+        g = mk().arith("fast").run()
+        o = oracle.run_solver(mk())
+        n = g.trace_n[0]
+        assert np.array_equal(g.trace_t[0, :n], o.trace_t[0, :n])
+        rel = np.max(np.abs(g.trace_p[0, :n] - o.trace_p[0, :n]) / np.maximum(np.abs(o.trace_p[0, :n]), 1e-3))
+        assert rel < 1e-12, rel
+
+
+def test_fibonacci_periodic_events(oracle):
+    # examples/ode-linear-3-fibonacci.rs: Periodic(1) fires at t = 1..49, x(n) = F_n
+    g, o = run_both(oracle, cases.fibonacci)
+    assert_same_counters(g, o)
+    assert_same_trace(g, o, exact=True)
+    assert np.array_equal(g.event_t, o.event_t)
+    ne = g.event_n[0]
+    assert list(g.event_t[0, :ne]) == [float(i) for i in range(1, 50)]
+    # x(10) = 55
+    n = g.trace_n[0]
+    i10 = list(g.trace_t[0, :n]).index(10.0)
+    assert abs(g.trace_p[0, i10, 0] - 55.0) < 1e-6
+
+
+# ---------------------------------------------------------------- events
+def test_bouncing_ball_strict_bit_exact(oracle):
+    mk = lambda: cases.bouncing_ball(n=96, t1=8.0, trace=d.Trace(1, 2048))
+    g, o = run_both(oracle, mk)
+    assert_same_counters(g, o)
+    assert np.array_equal(g.event_n, o.event_n)
+    assert np.array_equal(g.event_t, o.event_t)          # bisection results, bit for bit
+    assert np.array_equal(g.event_index, o.event_index)
+    assert_same_trace(g, o, exact=True)
+    assert np.array_equal(g.p, o.p)
+    # the single-trajectory anchors of SURVEY §8c
+    g1 = cases.bouncing_ball().run()
+    impacts = g1.event_t[0, :g1.event_n[0]][g1.event_index[0, :g1.event_n[0]] == 1]
+    assert len(impacts) == 78 and g1.steps[0] + 1 == 1815
+    assert abs(impacts[0] - (-0.01 + math.sqrt(19.6001)) / 9.8) < 2e-15
+
+
+def test_bouncing_ball_batching_threshold_does_not_change_results():
+    res = []
+    for thr in ("1", "8", "32"):
+        os.environ["DFB_LOCATE_BATCH"] = thr
+        try:
+            res.append(cases.bouncing_ball(n=200, t1=6.0).run())
+        finally:
+            del os.environ["DFB_LOCATE_BATCH"]
+    for r in res[1:]:
+        assert np.array_equal(r.p, res[0].p) and np.array_equal(r.event_t, res[0].event_t)
+        assert np.array_equal(r.steps, res[0].steps)
+
+
+def test_bouncing_ball_fast_event_times_within_tolerance(oracle):
+    g = cases.bouncing_ball(n=64, t1=6.0, arith="fast").run()
+    o = oracle.run_solver(cases.bouncing_ball(n=64, t1=6.0), n_threads=8)
+    assert np.array_equal(g.event_n, o.event_n)
+    assert np.array_equal(g.event_index, o.event_index)
+    assert np.max(np.abs(g.event_t - o.event_t)) < 1e-11
+    assert np.max(np.abs(g.p - o.p)) < 1e-10
+
+
+def test_egg_billiard_strict_bit_exact(oracle):
+    mk = lambda: cases.egg_billiard(n=64, reflections=60)
+    g, o = run_both(oracle, mk)
+    assert_same_counters(g, o)
+    assert np.all(g.status == d.abi.TRAJ_STOPPED)
+    assert np.all(np.isinf(g.t))
+    assert np.array_equal(g.event_t, o.event_t)
+    assert np.array_equal(g.p, o.p)
+    assert np.array_equal(g.aux, o.aux) and np.all(g.aux[:, 0] == 60.0)
+    g1 = cases.egg_billiard(reflections=200).run()
+    assert g1.steps[0] + 1 == 1497  # SURVEY §8c anchor
+
+
+def test_relay_msign_strict_bit_exact(oracle):
+    g, o = run_both(oracle, cases.relay_msign)
+    assert_same_counters(g, o)
+    assert_same_trace(g, o, exact=True)
+    assert np.array_equal(g.event_t, o.event_t)
+    # analytic solution of examples/ode-2-relay-msign.rs:8-13 at the recorded times
+    n = g.trace_n[0]
+    t = g.trace_t[0, :n]
+    sgn = np.sign((t * 0.5) % 1.0 - 0.5)
+    x = (t - np.floor(t)) * (t - np.ceil(t)) * sgn
+    assert np.max(np.abs(g.trace_p[0, :n, 0] - x)) < 1e-9
+
+
+@pytest.mark.parametrize("detection,location", [
+    (d.abi.DET_ZERO, d.abi.LOCATE_LERP), (d.abi.DET_ZERO, d.abi.LOCATE_REGULA_FALSI),
+    (d.abi.DET_ZERO, d.abi.LOCATE_STEP_BEGIN), (d.abi.DET_ZERO, d.abi.LOCATE_STEP_END),
+    (d.abi.DET_ABOVE_ZERO, d.abi.LOCATE_BISECTION), (d.abi.DET_BELOW_ZERO, d.abi.LOCATE_BISECTION),
+    (d.abi.DET_SWITCH, d.abi.LOCATE_BISECTION_BOOL), (d.abi.DET_SWITCH_TRUE, d.abi.LOCATE_BISECTION_BOOL),
+    (d.abi.DET_SWITCH_FALSE, d.abi.LOCATE_BISECTION_BOOL)])
+def test_all_detection_and_location_methods(oracle, detection, location):
+    # harmonic-like relay system, every detection/location kind the reference defines
+    def mk():
+        s = (d.Solver.new().initial([0.25, 0.0]).equation(d.systems.RelayMsign).interval(0.5, 6.5)
+             .stepsize(0.09).log_events(d.EventLog(64)).on_step(d.Trace(1, 256)))
+        loc = d.Locator._mk("x", detection, location)
+        return s.on(loc, None)
+    g, o = run_both(oracle, mk)
+    assert_same_counters(g, o)
+    assert np.array_equal(g.event_t, o.event_t)
+    assert_same_trace(g, o, exact=True)
+
+
+def test_filters_every_separated_in_interval(oracle):
+    for flt in (lambda L: L.every(3), lambda L: L.separated_by(2.5), lambda L: L.in_interval(2.0, 5.0)):
+        def mk():
+            return (d.Solver.new().initial([0.25, 0.0]).equation(d.systems.RelayMsign)
+                    .interval(0.5, 10.5).stepsize(0.09).log_events(d.EventLog(64))
+                    .on(flt(d.Locator.zero("x")), None).on_step(d.Trace(1, 256)))
+        g, o = run_both(oracle, mk)
+        assert_same_counters(g, o)
+        assert np.array_equal(g.event_t, o.event_t)
+        assert g.event_n[0] > 0
+
+
+# ---------------------------------------------------------------- DDE / NDDE
+def test_dde_constant_history_strict_bit_exact(oracle):
+    # x' = a x + b x(t - 1) with constant history: no transcendental call anywhere
+    def mk():
+        prm = np.stack([np.linspace(-1.0, 0.5, 40), np.linspace(-2.0, -0.5, 40), np.ones(40), np.zeros(40)], 1)
+        return (d.Solver.new().max_delay(1.0).initial(np.ones((40, 1))).interval(0.0, 6.0)
+                .stepsize(0.02).equation(d.systems.DdeLinear, prm).on_step(d.Trace(1, 320)))
+    g, o = run_both(oracle, mk)
+    assert np.all(g.status == 0)
+    assert_same_counters(g, o)
+    assert_same_trace(g, o, exact=True)
+
+
+def test_dde_sin_reference_tolerance_and_oracle(oracle):
+    # tests/equation_types.rs:133: |x - sin t| < 1e-11; vs oracle: sin() differs by <= 2 ulp
+    for arith in ("strict", "fast"):
+        g = cases.eq_dde_sin(arith=arith).run()
+        assert g.status[0] == 0
+        n = g.trace_n[0]
+        assert n == 501
+        assert np.all(np.abs(g.trace_p[0, :n, 0] - np.sin(g.trace_t[0, :n])) < 1e-11)
+        o = oracle.run_solver(cases.eq_dde_sin())
+        assert np.array_equal(g.trace_t[0, :n], o.trace_t[0, :n])
+        assert np.max(np.abs(g.trace_p[0, :n] - o.trace_p[0, :n])) < 1e-13
+
+
+def test_dde_sin_ensemble_k_sweep(oracle):
+    k = 0.5 + np.arange(200) / 199.0
+    mk = lambda: cases.eq_dde_sin(k=k, t1=10.0, trace=False)
+    g, o = run_both(oracle, mk)
+    assert np.all(g.status == 0)
+    assert np.array_equal(g.steps, o.steps)
+    assert np.max(np.abs(g.p - o.p)) < 1e-13
+    assert np.max(np.abs(g.p[:, 0] - np.sin(k * 10.0))) < 1e-10
+
+
+def test_ndde_sin(oracle):
+    g = cases.eq_ndde_sin().run()
+    n = g.trace_n[0]
+    assert g.status[0] == 0 and n == 501
+    assert np.all(np.abs(g.trace_p[0, :n, 0] - np.sin(g.trace_t[0, :n])) < 1e-11)  # :155
+    o = oracle.run_solver(cases.eq_ndde_sin())
+    assert np.max(np.abs(g.trace_p[0, :n] - o.trace_p[0, :n])) < 1e-13
+
+
+def test_dde_panics_become_status_bits(oracle):
+    s = lambda: cases.eq_dde_sin().stepsize(1.5)           # delay <= h  (state.rs:172-177)
+    g, o = run_both(oracle, s)
+    assert g.status[0] & d.abi.TRAJ_HISTORY_NOT_READY and o.status[0] & d.abi.TRAJ_HISTORY_NOT_READY
+    s = lambda: cases.eq_ndde_sin().initial(d.InitFn(d.SIN))  # no derivative (initial_condition.rs:33)
+    g, o = run_both(oracle, s)
+    assert g.status[0] & d.abi.TRAJ_NO_DERIVATIVE and o.status[0] & d.abi.TRAJ_NO_DERIVATIVE
+    s = lambda: cases.eq_dde_sin().max_delay(0.5)           # window shorter than the delay (state.rs:166-171)
+    g, o = run_both(oracle, s)
+    assert g.status[0] & d.abi.TRAJ_HISTORY_DELETED and o.status[0] & d.abi.TRAJ_HISTORY_DELETED
+
+
+def test_dde_relay_clamp_strict_bit_exact(oracle):
+    mk = lambda: cases.dde_relay_clamp(t1=20.0)
+    g, o = run_both(oracle, mk)
+    assert g.status[0] == 0
+    assert_same_counters(g, o)
+    assert np.array_equal(g.event_t, o.event_t) and np.array_equal(g.event_index, o.event_index)
+    assert_same_trace(g, o, exact=True)
+    assert g.events[0] > 10
+
+
+# ---------------------------------------------------------------- adaptive
+def auto_stepsize(n_state, tol=1e-9):
+    return d.AutomaticStepsize(stepsize=1e-2, stepsize_range=(1e-6, 1e-1), atol=[tol] * n_state,
+                               rtol=[tol] * n_state, order=4, fac=0.9, fac_range=(0.2, 5.0))
+
+
+def test_adaptive_harmonic_vs_oracle(oracle):
+    # AutomaticStepsize is exercised by no reference test ("parity unpinned" upstream);
+    # pow() of CUDA and glibc agree to <= 2 ulp, so step sequences agree to tolerance.
+    def mk(arith="strict"):
+        return (d.Solver.new().initial(np.tile([0.0, 1.0], (33, 1))).equation(d.systems.Harmonic)
+                .interval(0.0, 10.0).stepsize(auto_stepsize(2)).on_step(d.Trace(1, 4096)).arith(arith))
+    g, o = run_both(oracle, mk)
+    assert np.all(g.status == 0)
+    assert np.array_equal(g.steps, o.steps) and np.array_equal(g.rejected, o.rejected)
+    n = g.trace_n[0]
+    assert np.max(np.abs(g.trace_t[0, :n] - o.trace_t[0, :n])) < 1e-10
+    assert np.max(np.abs(g.p - o.p)) < 1e-10
+    assert np.max(np.abs(g.p[:, 0] - math.sin(10.0))) < 1e-6
+    assert g.rejected[0] > 0 or g.steps[0] < 10.0 / 1e-2  # the controller actually adapts
+    f = mk("fast").run()
+    assert np.max(np.abs(f.p - o.p)) < 1e-9
+
+
+def test_adaptive_lorenz_short(oracle):
+    def mk():
+        return cases.lorenz(n=65, t1=2.0).stepsize(auto_stepsize(3))
+    g, o = run_both(oracle, mk)
+    assert np.all(g.status == 0)
+    assert np.max(np.abs(g.steps.astype(np.int64) - o.steps.astype(np.int64))) <= 1
+    assert np.max(np.abs(g.p - o.p) / np.maximum(np.abs(o.p), 1.0)) < 1e-7
+
+
+# ---------------------------------------------------------------- Lyapunov
+def test_lyapunov_scalar(oracle):
+    lam = [-5., -4., -3., -2., -1., 1., 2., 3., 4., 5.]
+    for tmax in (10., 100., 1000.):
+        g = cases.lyap_linear_1_const(lam, tmax).run()
+        assert np.all(np.abs(np.array(lam) - g.aux[:, 0] / tmax) < 2.0 / tmax)   # lyapunov_exponents.rs:42
+        o = oracle.run_solver(cases.lyap_linear_1_const(lam, tmax))
+        assert np.array_equal(g.steps, o.steps) and np.array_equal(g.p, o.p)
+        assert np.max(np.abs(g.aux - o.aux)) < 1e-9 * tmax
+        g = cases.lyap_linear_1_sin(lam, tmax).run()
+        assert np.all(np.abs(np.array(lam) - g.aux[:, 0] / tmax) < 10.0 / tmax)  # :80
+
+
+def test_lyapunov_matrix(oracle):
+    real = [[2., 0., -2.], [3., 1., -2.], [5., 3., -2.], [3., 2., 1.], [4., -1., -1.]]
+    mats = [cases.real_jordan_matrix(e) for e in real]
+    for tmax in (10., 100.):
+        g = cases.lyap_linear_3(mats, tmax).run()
+        o = oracle.run_solver(cases.lyap_linear_3(mats, tmax))
+        assert np.array_equal(g.steps, o.steps)
+        assert np.array_equal(g.p, o.p)  # Householder QR: sqrt and division are IEEE on both sides
+        for e, l in zip(real, g.aux / tmax):
+            tol = 40.0 if (e[0] == e[1] or e[1] == e[2]) else 2.0
+            assert np.max(np.abs(np.array(e) - l)) < tol / tmax                  # :161
+
+
+def test_lyapunov_lorenz(oracle):
+    # tests/lyapunov_exponents.rs:243-311 at tmax = 100 and 1000; oracle within 1e-3 (north_star)
+    ref = np.array([0.90566, 0.0, -14.57233])
+    for tmax in (100., 1000.):
+        g = cases.lyap_lorenz(tmax).run()
+        assert g.status[0] == 0
+        lam = g.aux[0] / tmax
+        assert np.max(np.abs(lam - ref)) < 0.00007 + 50.0 / tmax
+    o = oracle.run_solver(cases.lyap_lorenz(100.))
+    g = cases.lyap_lorenz(100.).run()
+    assert np.array_equal(g.steps, o.steps) and g.events[0] == 200 and g.steps[0] + 1 == 20119
+    assert np.max(np.abs(g.aux[0] / 100. - o.aux[0] / 100.)) < 1e-3
+    f = cases.lyap_lorenz(100., arith="fast").run()
+    assert np.max(np.abs(f.aux[0] / 100. - o.aux[0] / 100.)) < 1e-3
+    # a rho grid, one trajectory per rho
+    rho = np.linspace(25.0, 35.0, 40)
+    gg = cases.lyap_lorenz(50., rho=rho).run()
+    assert np.all(gg.status == 0) and np.all(gg.aux[:, 0] / 50. > 0.3)  # chaotic band
+
+
+# ---------------------------------------------------------------- full-size properties
+def test_full_size_lorenz_properties():
+    # BASELINE config 2 at full size (2^20 members, t in [0,50], h = 1/250, rktp64, FAST)
+    n = 1 << 20
+    rho = 20.0 + 20.0 * np.arange(n) / (n - 1)
+    rho[n // 2:] = rho[: n // 2]          # duplicate the first half: identical inputs -> identical bits
+    g = cases.lorenz(n=n, t1=50.0, arith="fast", rho=rho).run()
+    assert np.all(g.status == 0)
+    assert np.all(g.steps == 12500) and np.all(g.rhs_evals == 12500 * 7 + 1)
+    assert np.all(g.t == g.t[0]) and abs(g.t[0] - 50.0) < 1e-9
+    assert np.array_equal(g.p[: n // 2], g.p[n // 2:])
+    assert np.all(np.isfinite(g.p)) and np.max(np.abs(g.p)) < 200.0   # stays on the attractor
+    again = cases.lorenz(n=n, t1=50.0, arith="fast", rho=rho).run()
+    assert np.array_equal(again.p, g.p)                               # deterministic
+
+
+def test_full_size_linearity_property():
+    # y' = A y is linear: scaling y0 by a power of two scales the result exactly, in both arithmetics
+    n = 1 << 18
+    rng = np.random.default_rng(7)
+    a = rng.uniform(-1.0, 1.0, size=(n, 9))
+    y0 = rng.uniform(-1.0, 1.0, size=(n, 3))
+    for arith in ("strict", "fast"):
+        mk = lambda s: (d.Solver.new().initial(y0 * s).equation(d.systems.Linear3, a)
+                        .interval(0.0, 2.0).stepsize(0.01).arith(arith))
+        g1, g4 = mk(1.0).run(), mk(4.0).run()
+        assert np.array_equal(g1.p * 4.0, g4.p)

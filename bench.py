@@ -5,7 +5,7 @@ fixed h = 1/250, t in [0, 50]  (BASELINE.json configs[1], SURVEY.md §8d config 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 One "step" = one full pass of the hot path over the ensemble: every member is
-integrated from t = 0 to t = 50 (12 500 RK steps each).  `value` is RK steps/s with
+integrated from t = 0 to t = 50 (12 501 RK steps each).  `value` is RK steps/s with
 inputs resident in HBM (CUDA events, max over ranks); `e2e` is the same metric
 through the C ABI with host buffers (pinned H2D of y0/params and D2H of the final
 states inside the timed region).  Under torchrun each rank integrates its own
@@ -34,7 +34,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 N_MEMBERS = 1 << 20
 T_END = 50.0
 H = 1.0 / 250.0
-STEPS_PER_MEMBER = 12500
+STEPS_PER_MEMBER = 12501  # 12500 x (1/250) accumulates to one ulp short of 50, then one closing step
 FLOPS_PER_STEP = 252.0  # Lorenz + rktp64, FMA = 2, structural zeros skipped
 WORKLOAD = "lorenz_2^20_members_rho_sweep_rktp64_h=1/250_t=[0,50]"
 
@@ -289,7 +289,7 @@ def main():
     cpu1_rate, _, _ = cpu_oracle_rate(64, 1)
     cpu_baseline = {
         "value": cpu_rate, "unit": "RK steps/s", "cores": cores, "kind": "port",
-        "sample": f"{n_sample} members x 12500 steps ({cpu_dt:.1f} s), C++ restatement of the reference "
+        "sample": f"{n_sample} members x 12501 steps ({cpu_dt:.1f} s), C++ restatement of the reference "
                   f"CPU path (Rust toolchain unavailable), std::thread over members",
         "single_core_ns_per_step": 1e9 / cpu1_rate,
     }

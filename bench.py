@@ -115,6 +115,60 @@ def cpu_oracle_rate(n_sample, threads):
     return steps / dt, dt, steps
 
 
+DDE_MEMBERS = 1 << 18
+DDE_BYTES_PER_STEP = 96.0  # one 48-byte coefficient record written + read per RK step (N=1, I=5)
+
+
+def dde_leg(d, torch, local_rank, K=3, W=2):
+    """Secondary workload (BASELINE configs[2]): 2^18-member constant-delay DDE
+    x' = a x + b x(t-1), k sweep, rktp64, h = 0.02, t in [0, 100]; HBM-bound."""
+    import cases
+    n = DDE_MEMBERS
+    k = 0.5 + np.arange(n) / (n - 1.0)
+    prm = cases.dde_params(k)
+    problem = (d.Solver.new().max_delay(1.0).initial(d.InitFn(d.SIN)).interval(0.0, 100.0)
+               .stepsize(0.02).equation(d.systems.DdeLinear, prm).arith("fast").problem())
+    ens = d.Ensemble(problem, n, device=local_rank)
+    d_prm = torch.from_numpy(np.ascontiguousarray(prm.T)).cuda()
+    d_y0 = torch.zeros(n, dtype=torch.float64, device="cuda")
+    ens.set_initial_device(d_y0.data_ptr())
+    ens.set_params_device(d_prm.data_ptr())
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(W):
+        ens.run(stream)
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(K):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ens.run(stream)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    tot = ens.totals()
+    t_fin, y_fin, _ = ens.final()
+    err = float(np.max(np.abs(y_fin[:, 0] - np.sin(k * t_fin))))
+    steps = tot["steps"]
+    rate = steps / (float(np.mean(ms)) * 1e-3)
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        hbm, src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        hbm, src = 6650.0, "fallback 6.65 TB/s (of fallback)"
+    achieved = DDE_BYTES_PER_STEP * rate / 1e9
+    ens.close()
+    return {
+        "workload": "dde_linear_2^18_members_k_sweep_tau=1_rktp64_h=0.02_t=[0,100]",
+        "metric": "rk_steps_per_sec", "value": rate, "unit": "RK steps/s", "ms_per_step": float(np.mean(ms)),
+        "rk_steps_per_member": int(steps // n), "n_failed": int(tot["n_failed"]),
+        "max_abs_err_vs_exact_sin": err,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                     "frac": achieved / hbm, "traffic": None, "peak_source": src,
+                     "algorithmic_bytes_per_rk_step": DDE_BYTES_PER_STEP,
+                     "kernel": "dde_fixed_kernel<SysDdeLinear,7,5,rktp64-sparsity>"},
+    }
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return 0
@@ -294,6 +348,13 @@ def main():
         "single_core_ns_per_step": 1e9 / cpu1_rate,
     }
 
+    secondary = None
+    if world == 1 and not os.environ.get("DFB_BENCH_SKIP_DDE"):
+        try:
+            secondary = dde_leg(d, torch, local_rank)
+        except Exception as e:  # the headline line must still print
+            secondary = {"error": repr(e)}
+
     line = {
         "metric": "rk_steps_per_sec", "value": value, "unit": "RK steps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": max_ms / K,
@@ -310,6 +371,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "wall_s_timed_region": t_wall,
+        "secondary_dde": secondary,
     }
     print(json.dumps(line))
     if world > 1:

@@ -36,6 +36,15 @@ int run_ode_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t
                        uint32_t* status, cudaStream_t stream);
 }
 
+namespace dfb_fast {
+int run_dde_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h,
+                       double max_delay, int history_id, int ring_capacity, size_t n,
+                       const double* y0, const double* params, double* ring, double* t_final,
+                       double* y_final, unsigned long long* steps, unsigned long long* rhs_evals,
+                       uint32_t* status, cudaStream_t stream);
+size_t dde_fixed_ring_doubles(int n_state, int I, int capacity);
+}
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -93,28 +102,26 @@ __global__ void soa_to_aos_kernel(const double* __restrict__ src, double* __rest
   for (int c = 0; c < width; ++c) dst[i * width + c] = src[size_t(c) * n + i];
 }
 
-// ---- FP64 peak microbenchmark: 8 independent DFMA chains per thread
+// ---- FP64 peak microbenchmark: CHAINS independent DFMA chains per thread
+template <int CHAINS>
 __global__ void __launch_bounds__(256) dfma_chain_kernel(double* out, int iters, double a, double b,
                                                          long long* cycles) {
-  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
-         x6 = x0 + 6, x7 = x0 + 7;
+  double x[CHAINS];
+#pragma unroll
+  for (int c = 0; c < CHAINS; ++c) x[c] = threadIdx.x * 1e-3 + c;
   const long long c0 = clock64();
 #pragma unroll 1
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      x0 = fma(x0, a, b);
-      x1 = fma(x1, a, b);
-      x2 = fma(x2, a, b);
-      x3 = fma(x3, a, b);
-      x4 = fma(x4, a, b);
-      x5 = fma(x5, a, b);
-      x6 = fma(x6, a, b);
-      x7 = fma(x7, a, b);
-    }
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int c = 0; c < CHAINS; ++c) x[c] = fma(x[c], a, b);
   }
   const long long c1 = clock64();
-  out[size_t(blockIdx.x) * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  double s = 0.0;
+#pragma unroll
+  for (int c = 0; c < CHAINS; ++c) s += x[c];
+  out[size_t(blockIdx.x) * blockDim.x + threadIdx.x] = s;
   if (blockIdx.x == 0 && threadIdx.x == 0) *cycles = c1 - c0;
 }
 
@@ -150,6 +157,8 @@ struct dfb_handle {
   int32_t* d_ev_idx = nullptr;
   uint32_t* d_nevents = nullptr;
   double *d_ring_t = nullptr, *d_ring_y = nullptr, *d_ring_k = nullptr;
+  double* d_ring_coeff = nullptr;  // coefficient-record ring of the DDE hot-path kernel
+  bool dde_hot = false;
   double* d_disco_t = nullptr;
   int32_t* d_disco_ord = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -172,7 +181,7 @@ void free_all(dfb_handle* h) {
                   h->d_aux,     h->d_steps,   h->d_rejected, h->d_events,  h->d_rhs,
                   h->d_status,  h->d_trace_t, h->d_trace_y,  h->d_nsamples, h->d_ev_t,
                   h->d_ev_idx,  h->d_nevents, h->d_ring_t,   h->d_ring_y,  h->d_ring_k,
-                  h->d_disco_t, h->d_disco_ord};
+                  h->d_disco_t, h->d_disco_ord, h->d_ring_coeff};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -373,7 +382,26 @@ int dfb_create(const dfb_problem* desc, size_t n_traj, int device, dfb_handle** 
     H_ALLOC(h->d_ev_idx, n * size_t(desc->event_capacity));
     H_ALLOC(h->d_nevents, n);
   }
-  if (info->uses_history) {
+  // Constant-delay DDE hot path (dev/dde_fixed.cuh): FAST arithmetic, fixed step, no
+  // locators, final state only, one of the compiled tableau shapes.
+  {
+    const int S_ = desc->rk.S, I_ = desc->rk.I;
+    const bool shape_ok = (S_ == 7 && I_ == 5) || (S_ == 5 && I_ == 4) || (S_ == 4 && I_ == 2);
+    h->dde_hot = info->uses_history && desc->arith == DFB_ARITH_FAST &&
+                 desc->stepsize_kind == DFB_STEP_FIXED && desc->n_loc == 0 && desc->n_disco == 0 &&
+                 desc->trace_every == 0 && desc->max_steps == 0 && shape_ok &&
+                 (desc->system_id == DFB_SYS_DDE_LINEAR || desc->system_id == DFB_SYS_NDDE_LINEAR) &&
+                 std::isfinite(desc->max_delay) && desc->max_delay > 0.0 &&
+                 desc->max_delay / desc->h < 60000.0 && !std::getenv("DFB_FORCE_GENERAL");
+  }
+  if (h->dde_hot) {
+    // records the reference's deque can hold: ceil(max_delay / h) + 3; + window/prefetch slack
+    size_t cap = size_t(desc->ring_capacity);
+    if (cap == 0) cap = size_t(std::ceil(desc->max_delay / desc->h)) + 8;
+    cap = next_pow2(cap);
+    h->ring_capacity = int(cap);
+    H_ALLOC(h->d_ring_coeff, n * dfb_fast::dde_fixed_ring_doubles(N, desc->rk.I, int(cap)));
+  } else if (info->uses_history) {
     size_t cap = size_t(desc->ring_capacity);
     if (cap == 0) {
       // window of the reference's deque: ceil(max_delay / h) + 3 records, plus two
@@ -491,6 +519,23 @@ int dfb_run(dfb_handle* h, void* stream_v) {
       return DFB_OK;
     }
     // rc == -1: no specialised kernel -> general path below
+  }
+
+  if (h->dde_hot) {
+    DFB_CUDA(cudaMemsetAsync(h->d_rejected, 0, n * sizeof(unsigned long long), stream));
+    DFB_CUDA(cudaMemsetAsync(h->d_events, 0, n * sizeof(unsigned long long), stream));
+    DFB_CUDA(cudaEventRecord(h->ev0, stream));
+    const int rc = dfb_fast::run_dde_fixed_shim(p.system_id, p.rk, p.t0, p.t1, p.h, p.max_delay,
+                                                p.history_id, h->ring_capacity, n, y0, params,
+                                                h->d_ring_coeff, h->d_t, h->d_y, h->d_steps, h->d_rhs,
+                                                h->d_status, stream);
+    if (rc > 0) return fail(DFB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(cudaError_t(rc)));
+    if (rc < 0) return fail(DFB_ERR_UNSUPPORTED, "no DDE hot-path kernel for this tableau");
+    DFB_CUDA(cudaEventRecord(h->ev1, stream));
+    h->launches = 1;
+    h->used_hot_path = true;
+    h->ran = true;
+    return DFB_OK;
   }
 
   DevProblem P;
@@ -746,30 +791,46 @@ int dfb_measure_fp64_peak(int device, double* tflops, double* sm_mhz_est) {
   DFB_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
   DFB_CUDA(cudaGetDeviceProperties(&prop, device));
-  const int block = 256, blocks = prop.multiProcessorCount * 8;
-  const int iters = 4096;
+  const int block = 256;
+  const int max_blocks = prop.multiProcessorCount * 8;
+  const int iters = 8192;  // >= 4 ms per launch: clocks are at their steady state
   double* d_out = nullptr;
   long long* d_cyc = nullptr;
-  DFB_CUDA(cudaMalloc(&d_out, size_t(block) * blocks * 8));
+  DFB_CUDA(cudaMalloc(&d_out, size_t(block) * max_blocks * 8));
   DFB_CUDA(cudaMalloc(&d_cyc, 8));
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  float best = 1e30f;
-  for (int rep = 0; rep < 6; ++rep) {
-    cudaEventRecord(e0);
-    dfma_chain_kernel<<<blocks, block>>>(d_out, iters, 0.999999, 1e-7, d_cyc);
-    cudaEventRecord(e1);
-    DFB_CUDA(cudaEventSynchronize(e1));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    if (rep >= 2 && ms < best) best = ms;
+  double best_tf = 0.0, mhz = 0.0;
+  // sweep resident blocks per SM x chains per thread; keep the best rate
+  for (int per_sm = 1; per_sm <= 8; per_sm *= 2) {
+    for (int chains = 8; chains <= 16; chains *= 2) {
+      const int blocks = prop.multiProcessorCount * per_sm;
+      float best_ms = 1e30f;
+      for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        if (chains == 4) dfma_chain_kernel<4><<<blocks, block>>>(d_out, iters, 0.999999, 1e-7, d_cyc);
+        else if (chains == 8) dfma_chain_kernel<8><<<blocks, block>>>(d_out, iters, 0.999999, 1e-7, d_cyc);
+        else dfma_chain_kernel<16><<<blocks, block>>>(d_out, iters, 0.999999, 1e-7, d_cyc);
+        cudaEventRecord(e1);
+        DFB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep >= 1 && ms < best_ms) best_ms = ms;
+      }
+      const double flops = 2.0 * 8.0 * chains * double(iters) * double(block) * double(blocks);
+      const double tf = flops / (double(best_ms) * 1e-3) / 1e12;
+      if (tf > best_tf) best_tf = tf;
+      if (per_sm == 1 && chains == 16) {
+        // one block per SM: block 0 spans the whole launch, so its cycle count / time = SM clock
+        long long cyc = 0;
+        DFB_CUDA(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost));
+        mhz = double(cyc) / (double(best_ms) * 1e-3) / 1e6;
+      }
+    }
   }
-  long long cyc = 0;
-  DFB_CUDA(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost));
-  const double flops = 2.0 * 64.0 * double(iters) * double(block) * double(blocks);
-  if (tflops) *tflops = flops / (double(best) * 1e-3) / 1e12;
-  if (sm_mhz_est) *sm_mhz_est = double(cyc) / (double(best) * 1e-3) / 1e6;
+  if (tflops) *tflops = best_tf;
+  if (sm_mhz_est) *sm_mhz_est = mhz;
   cudaFree(d_out);
   cudaFree(d_cyc);
   cudaEventDestroy(e0);

@@ -13,6 +13,7 @@
 // then the parked lanes run their bisections together (warp-level batching).
 #pragma once
 #include "common.cuh"
+#include "history_fn.cuh"
 #include "systems.cuh"
 
 namespace DFB_NS {
@@ -103,33 +104,7 @@ struct History {
   // InitialCondition::eval::<D> (initial_condition.rs:15-50)
   template <int D>
   __device__ void init_eval(double t, double* out) {
-#pragma unroll
-    for (int n = 0; n < N; ++n) out[n] = 0.0;
-    switch (P->history_id) {
-      case DFB_HIST_CONSTANT:
-        if (D == 0) {
-#pragma unroll
-          for (int n = 0; n < N; ++n) out[n] = y0[n];
-        }
-        break;
-      case DFB_HIST_SIN:
-        out[0] = D == 0 ? sin(hist_k * t) : hist_k * cos(hist_k * t);
-        break;
-      case DFB_HIST_SIN_NODERIV:
-        if (D == 0) out[0] = sin(hist_k * t);
-        else {
-          status |= DFB_TRAJ_NO_DERIVATIVE;
-          out[0] = dev_nan();
-        }
-        break;
-      case DFB_HIST_INV_SQUARE:
-        if (D == 0) out[0] = 1.0 / (t * t);
-        else {
-          status |= DFB_TRAJ_NO_DERIVATIVE;
-          out[0] = dev_nan();
-        }
-        break;
-    }
+    init_condition_eval<D, N>(P->history_id, t, y0, hist_k, status, out);
   }
 
   template <int D>

@@ -276,6 +276,8 @@ struct SysZero1 : SysBase {  // tests/delay_propagation.rs:13, :86
 struct SysDdeLinear : SysBase {  // tests/equation_types.rs:131
   static constexpr int ID = DFB_SYS_DDE_LINEAR, N = 1, NP = 4;
   static constexpr bool uses_history = true;
+  // the one constant delay of this equation (lets the streaming-window kernel take it)
+  __device__ __forceinline__ static double const_delay(const double* prm) { return prm[2]; }
   template <class V>
   __device__ __forceinline__ static void rhs(const V& s, const double* prm, double* out) {
     double del[1];
@@ -287,6 +289,7 @@ struct SysDdeLinear : SysBase {  // tests/equation_types.rs:131
 struct SysNddeLinear : SysBase {  // tests/equation_types.rs:150
   static constexpr int ID = DFB_SYS_NDDE_LINEAR, N = 1, NP = 4;
   static constexpr bool uses_history = true;
+  __device__ __forceinline__ static double const_delay(const double* prm) { return prm[2]; }
   template <class V>
   __device__ __forceinline__ static void rhs(const V& s, const double* prm, double* out) {
     double del[1], ddel[1];

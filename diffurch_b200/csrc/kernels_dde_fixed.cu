@@ -1,0 +1,118 @@
+// Instantiations + launcher of the constant-delay DDE hot-path kernel (FAST
+// arithmetic only; STRICT goes through the general integrator, which keeps the
+// reference's record format and operation order).
+#include "dev/dde_fixed.cuh"
+
+#include <cmath>
+#include <cstring>
+
+namespace DFB_NS {
+namespace {
+constexpr int kBlock = 128;
+
+constexpr unsigned long long bit8(int i, int j) { return 1ull << (i * 8 + j); }
+constexpr unsigned long long full_lower(int S) {
+  unsigned long long m = 0;
+  for (int i = 1; i < S; ++i)
+    for (int j = 0; j < i; ++j) m |= bit8(i, j);
+  return m;
+}
+constexpr unsigned long long full_bi(int S, int I) {
+  unsigned long long m = 0;
+  for (int i = 0; i < S; ++i)
+    for (int j = 1; j < I; ++j) m |= bit8(i, j);
+  return m;
+}
+// rktp64 (rk.rs:313-429): row 0 -> theta^1..4, rows 2,3,4,6 -> theta^2..4, row 5 -> theta^4, row 1 zero
+constexpr unsigned long long kBiRktp64 =
+    bit8(0, 1) | bit8(0, 2) | bit8(0, 3) | bit8(0, 4) | bit8(2, 2) | bit8(2, 3) | bit8(2, 4) |
+    bit8(3, 2) | bit8(3, 3) | bit8(3, 4) | bit8(4, 2) | bit8(4, 3) | bit8(4, 4) | bit8(5, 4) |
+    bit8(6, 2) | bit8(6, 3) | bit8(6, 4);
+
+template <class Sys, int S, int I, unsigned long long AMASK, unsigned BMASK, unsigned long long BIMASK>
+bool try_launch(int S_rt, int I_rt, unsigned long long am, unsigned bm, unsigned long long bim,
+                const DdeFixedArgs& A, cudaStream_t stream, int* rc) {
+  if (S_rt != S || I_rt != I) return false;
+  if ((am & ~AMASK) || (bm & ~BMASK) || (bim & ~BIMASK)) return false;
+  const size_t grid = (A.n_traj + kBlock - 1) / kBlock;
+  dde_fixed_kernel<Sys, S, I, AMASK, BMASK, BIMASK, kBlock><<<unsigned(grid), kBlock, 0, stream>>>(A);
+  *rc = int(cudaGetLastError());
+  return true;
+}
+
+template <class Sys>
+bool launch_sys(int S, int I, unsigned long long am, unsigned bm, unsigned long long bim,
+                const DdeFixedArgs& A, cudaStream_t st, int* rc) {
+  return try_launch<Sys, 7, 5, full_lower(7), 0x7Du, kBiRktp64>(S, I, am, bm, bim, A, st, rc) ||
+         try_launch<Sys, 7, 5, full_lower(7), 0x7Fu, full_bi(7, 5)>(S, I, am, bm, bim, A, st, rc) ||
+         try_launch<Sys, 5, 4, full_lower(5), 0x1Fu, full_bi(5, 4)>(S, I, am, bm, bim, A, st, rc) ||
+         try_launch<Sys, 4, 2, full_lower(4), 0xFu, full_bi(4, 2)>(S, I, am, bm, bim, A, st, rc);
+}
+}  // namespace
+
+// Bytes of ring the kernel needs per trajectory for (N, I, capacity).
+size_t dde_fixed_ring_doubles(int n_state, int I, int capacity) {
+  return size_t(capacity) * size_t(1 + n_state * I);
+}
+
+// returns 0 = launched, >0 = CUDA error code, -1 = no compiled kernel
+int run_dde_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h,
+                       double max_delay, int history_id, int ring_capacity, size_t n,
+                       const double* y0, const double* params, double* ring, double* t_final,
+                       double* y_final, unsigned long long* steps, unsigned long long* rhs_evals,
+                       uint32_t* status, cudaStream_t stream) {
+  DdeFixedArgs A;
+  std::memset(&A, 0, sizeof(A));
+  unsigned long long am = 0, bim = 0;
+  unsigned bm = 0;
+  for (int i = 0; i < DFB_MAX_STAGES; ++i) {
+    for (int j = 0; j < DFB_MAX_STAGES; ++j) {
+      const double a = rk.a[i * DFB_MAX_STAGES + j];
+      A.a[i * DFB_MAX_STAGES + j] = a;
+      A.ha[i * DFB_MAX_STAGES + j] = h * a;
+      if (i < rk.S && j < i && a != 0.0) am |= bit8(i, j);
+    }
+    A.b[i] = rk.b[i];
+    A.c[i] = rk.c[i];
+    A.hb[i] = h * rk.b[i];
+    A.hc[i] = rk.c[i] * h;
+    if (i < rk.S && rk.b[i] != 0.0) bm |= 1u << i;
+    double hp = 1.0;  // h^(j-1)
+    for (int j = 0; j < DFB_MAX_INTERP; ++j) {
+      const double v = rk.bi[i * DFB_MAX_INTERP + j];
+      A.bi[i * DFB_MAX_INTERP + j] = v;
+      if (j >= 1) {
+        A.bih[i * DFB_MAX_INTERP + j] = v / hp;
+        hp *= h;
+        if (i < rk.S && j < rk.I && v != 0.0) bim |= bit8(i, j);
+      } else if (i < rk.S && v != 0.0) {
+        return -1;  // b_i(0) != 0: not a continuous extension this kernel can pre-combine
+      }
+    }
+  }
+  A.t0 = t0;
+  A.t1 = t1;
+  A.h = h;
+  A.max_delay = max_delay;
+  A.history_id = history_id;
+  A.ring_capacity = ring_capacity;
+  A.n_traj = n;
+  A.y0 = y0;
+  A.params = params;
+  A.t_final = t_final;
+  A.y_final = y_final;
+  A.steps = steps;
+  A.rhs_evals = rhs_evals;
+  A.status = status;
+  A.ring = ring;
+  int rc = 0;
+  bool ok = false;
+  switch (system_id) {
+    case DFB_SYS_DDE_LINEAR: ok = launch_sys<SysDdeLinear>(rk.S, rk.I, am, bm, bim, A, stream, &rc); break;
+    case DFB_SYS_NDDE_LINEAR: ok = launch_sys<SysNddeLinear>(rk.S, rk.I, am, bm, bim, A, stream, &rc); break;
+    default: break;
+  }
+  return ok ? rc : -1;
+}
+
+}  // namespace DFB_NS

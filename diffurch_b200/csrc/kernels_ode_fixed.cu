@@ -3,6 +3,8 @@
 #include "dev/ode_fixed.cuh"
 #include "launch.hpp"
 
+#include <cstdlib>
+
 namespace DFB_NS {
 
 namespace {
@@ -10,14 +12,27 @@ constexpr unsigned long long kMaskRk4 = amask_bit(1, 0) | amask_bit(2, 1) | amas
 constexpr bool kPrescaled = (DFB_ARITH == 1);
 constexpr int kBlock = 128;
 
+// trajectories per thread: 2 where the doubled register footprint still fits
+// (N * (S + 3) doubles per trajectory), else 1.  DFB_ODE_TPT=1|2 overrides (tuning).
+template <class Sys, int S>
+constexpr int default_tpt() { return (Sys::N * (S + 3) <= 40) ? 2 : 1; }
+
 template <class Sys, int S, unsigned long long AMASK, unsigned BMASK>
 bool try_launch(int S_rt, unsigned long long amask, unsigned bmask, const OdeFixedArgs& A,
                 cudaStream_t stream, int* rc) {
   if (S_rt != S) return false;
   if ((amask & ~AMASK) != 0ull || (bmask & ~BMASK) != 0u) return false;  // kernel must cover every non-zero
-  const size_t grid = (A.n_traj + kBlock - 1) / kBlock;
-  ode_fixed_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock>
-      <<<unsigned(grid), kBlock, 0, stream>>>(A);
+  int tpt = default_tpt<Sys, S>();
+  if (const char* e = getenv("DFB_ODE_TPT")) tpt = atoi(e) == 2 ? 2 : 1;
+  if (Sys::N * (S + 3) > 40) tpt = 1;
+  const size_t per_block = size_t(kBlock) * tpt;
+  const size_t grid = (A.n_traj + per_block - 1) / per_block;
+  if (tpt == 2) {
+    if constexpr (Sys::N * (S + 3) <= 40)
+      ode_fixed_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 2><<<unsigned(grid), kBlock, 0, stream>>>(A);
+  } else {
+    ode_fixed_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 1><<<unsigned(grid), kBlock, 0, stream>>>(A);
+  }
   *rc = int(cudaGetLastError());
   return true;
 }

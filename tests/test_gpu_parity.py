@@ -302,6 +302,90 @@ def test_ndde_sin(oracle):
     assert np.max(np.abs(g.trace_p[0, :n] - o.trace_p[0, :n])) < 1e-13
 
 
+def test_dde_hot_path_fast_vs_oracle(oracle):
+    # FAST + fixed step + no trace -> the streaming-window kernel with pre-combined
+    # coefficient records (dev/dde_fixed.cuh).  Non-chaotic: within 1e-12 of the oracle.
+    k = 0.5 + np.arange(333) / 332.0          # ragged: 333 = 2 blocks + 77
+    for t1 in (0.5, 1.5, 10.0, 30.0):         # inside the history, across t = tau, long
+        mk = lambda arith: cases.eq_dde_sin(k=k, t1=t1, trace=False, arith=arith)
+        g = mk("fast").run()
+        o = oracle.run_solver(mk("strict"), n_threads=8)
+        assert np.all(g.status == 0)
+        assert np.array_equal(g.steps, o.steps) and np.array_equal(g.rhs_evals, o.rhs_evals)
+        assert np.array_equal(g.t, o.t)
+        assert np.max(np.abs(g.p - o.p)) < 1e-12, (t1, np.max(np.abs(g.p - o.p)))
+        assert np.max(np.abs(g.p[:, 0] - np.sin(k * t1))) < 1e-10
+    # the general kernel in FAST arithmetic agrees too (same inputs, forced)
+    os.environ["DFB_FORCE_GENERAL"] = "1"
+    try:
+        gen = cases.eq_dde_sin(k=k, t1=10.0, trace=False, arith="fast").run()
+    finally:
+        del os.environ["DFB_FORCE_GENERAL"]
+    hot = cases.eq_dde_sin(k=k, t1=10.0, trace=False, arith="fast").run()
+    assert np.max(np.abs(gen.p - hot.p)) < 1e-12
+
+
+def test_ndde_hot_path_fast_vs_oracle(oracle):
+    k = 0.5 + np.arange(130) / 129.0
+    def mk(arith):
+        return (d.Solver.new().initial(d.InitFn(d.SIN, d.SIN_DERIV))
+                .equation(d.systems.NddeLinear, cases.ndde_params(k)).interval(0.0, 10.0)
+                .max_delay(1.0).stepsize(0.02).arith(arith))
+    g = mk("fast").run()
+    o = oracle.run_solver(mk("strict"), n_threads=8)
+    assert np.all(g.status == 0) and np.array_equal(g.steps, o.steps)
+    assert np.max(np.abs(g.p - o.p)) < 1e-11
+    assert np.max(np.abs(g.p[:, 0] - np.sin(k * 10.0))) < 1e-9
+
+
+def test_dde_hot_path_other_tableaux_and_delays(oracle):
+    # rk43 (S=5, I=4 cubic interpolant), rk4 (linear interpolant), delays from 1.6 h to 40 h,
+    # constant history (no transcendental call)
+    for rk, h in (("rk43", 0.02), ("rk4", 0.01), ("rktp64", 0.05)):
+        for tau in (1.6 * h, 2.5 * h, 3.0 * h, 40.0 * h):
+            n = 70
+            prm = np.stack([np.linspace(-1.0, 0.5, n), np.linspace(-2.0, -0.5, n), np.full(n, tau), np.zeros(n)], 1)
+            def mk(arith):
+                return (d.Solver.new().max_delay(tau).initial(np.ones((n, 1))).interval(0.0, 3.0)
+                        .rk(d.RK.by_name(rk)).stepsize(h).equation(d.systems.DdeLinear, prm).arith(arith))
+            g = mk("fast").run()
+            o = oracle.run_solver(mk("strict"), n_threads=8)
+            assert np.all(o.status == 0) and np.all(g.status == 0), (rk, tau / h)
+            assert np.array_equal(g.steps, o.steps)
+            assert np.max(np.abs(g.p - o.p) / np.maximum(np.abs(o.p), 1.0)) < 1e-12, (rk, tau / h)
+
+
+def test_dde_hot_path_panics_become_status_bits(oracle):
+    mk = lambda: cases.eq_dde_sin(trace=False, arith="fast").stepsize(1.5)   # delay <= h
+    g, o = mk().run(), oracle.run_solver(mk())
+    assert g.status[0] & d.abi.TRAJ_HISTORY_NOT_READY and o.status[0] & d.abi.TRAJ_HISTORY_NOT_READY
+    mk = lambda: cases.eq_dde_sin(trace=False, arith="fast").max_delay(0.5)  # window < delay
+    g, o = mk().run(), oracle.run_solver(mk())
+    assert g.status[0] & d.abi.TRAJ_HISTORY_DELETED and o.status[0] & d.abi.TRAJ_HISTORY_DELETED
+    # a window only slightly shorter than the delay: the reference's prune rule
+    # (t_deque[1] < t_prev - max_delay) decides; the kernel replays it exactly
+    for md in (0.97, 0.985, 0.995, 1.0):
+        mk = lambda: cases.eq_dde_sin(trace=False, arith="fast", t1=4.0).max_delay(md)
+        g, o = mk().run(), oracle.run_solver(mk())
+        assert (g.status[0] & d.abi.TRAJ_HISTORY_DELETED) == (o.status[0] & d.abi.TRAJ_HISTORY_DELETED), md
+
+
+def test_full_size_dde_properties(oracle):
+    # BASELINE config 3 at full size: 2^18 members, k sweep, t in [0, 100]; the exact solution
+    # sin(k t) is the size-independent check, plus duplicated inputs -> identical bits
+    n = 1 << 18
+    k = 0.5 + np.arange(n) / (n - 1.0)
+    k[n // 2:] = k[: n // 2]
+    g = cases.eq_dde_sin(k=k, t1=100.0, trace=False, arith="fast").run()
+    assert np.all(g.status == 0)
+    assert np.all(g.steps == g.steps[0]) and 5000 <= g.steps[0] <= 5001
+    assert np.array_equal(g.p[: n // 2], g.p[n // 2:])
+    assert np.max(np.abs(g.p[:, 0] - np.sin(k * g.t))) < 1e-9
+    sub = slice(0, n, n // 64)
+    o = oracle.run_solver(cases.eq_dde_sin(k=k[sub], t1=100.0, trace=False), n_threads=8)
+    assert np.max(np.abs(g.p[sub] - o.p)) < 1e-11
+
+
 def test_dde_panics_become_status_bits(oracle):
     s = lambda: cases.eq_dde_sin().stepsize(1.5)           # delay <= h  (state.rs:172-177)
     g, o = run_both(oracle, s)

@@ -393,6 +393,12 @@ int dfb_create(const dfb_problem* desc, size_t n_traj, int device, dfb_handle** 
                  (desc->system_id == DFB_SYS_DDE_LINEAR || desc->system_id == DFB_SYS_NDDE_LINEAR) &&
                  std::isfinite(desc->max_delay) && desc->max_delay > 0.0 &&
                  desc->max_delay / desc->h < 60000.0 && !std::getenv("DFB_FORCE_GENERAL");
+    if (h->dde_hot) {  // the kernel indexes the ring with 32-bit offsets and counts steps in an int
+      const double cap_est = double(next_pow2(size_t(std::ceil(desc->max_delay / desc->h)) + 8));
+      const double steps_est = (desc->t1 - desc->t0) / desc->h;
+      if (cap_est * double((n + 31) / 32 * 32) * double(2 + N * desc->rk.I) >= 4.0e9 || !(steps_est < 2.0e9))
+        h->dde_hot = false;
+    }
   }
   if (h->dde_hot) {
     // records the reference's deque can hold: ceil(max_delay / h) + 3; + window/prefetch slack
@@ -400,7 +406,7 @@ int dfb_create(const dfb_problem* desc, size_t n_traj, int device, dfb_handle** 
     if (cap == 0) cap = size_t(std::ceil(desc->max_delay / desc->h)) + 8;
     cap = next_pow2(cap);
     h->ring_capacity = int(cap);
-    H_ALLOC(h->d_ring_coeff, n * dfb_fast::dde_fixed_ring_doubles(N, desc->rk.I, int(cap)));
+    H_ALLOC(h->d_ring_coeff, ((n + 31) / 32 * 32) * dfb_fast::dde_fixed_ring_doubles(N, desc->rk.I, int(cap)));
   } else if (info->uses_history) {
     size_t cap = size_t(desc->ring_capacity);
     if (cap == 0) {

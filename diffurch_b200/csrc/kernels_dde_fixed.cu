@@ -9,6 +9,7 @@
 namespace DFB_NS {
 namespace {
 constexpr int kBlock = 128;
+constexpr int kMinBlocks = 7;  // 7 x 128 threads: <= 72 registers; 2^18 members = 1.98 full waves on 148 SMs
 
 constexpr unsigned long long bit8(int i, int j) { return 1ull << (i * 8 + j); }
 constexpr unsigned long long full_lower(int S) {
@@ -35,7 +36,10 @@ bool try_launch(int S_rt, int I_rt, unsigned long long am, unsigned bm, unsigned
   if (S_rt != S || I_rt != I) return false;
   if ((am & ~AMASK) || (bm & ~BMASK) || (bim & ~BIMASK)) return false;
   const size_t grid = (A.n_traj + kBlock - 1) / kBlock;
-  dde_fixed_kernel<Sys, S, I, AMASK, BMASK, BIMASK, kBlock><<<unsigned(grid), kBlock, 0, stream>>>(A);
+  auto kernel = dde_fixed_kernel<Sys, S, I, AMASK, BMASK, BIMASK, kBlock, kMinBlocks>;
+  // the staging buffers of kMinBlocks resident blocks need the large shared-memory carveout
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  kernel<<<unsigned(grid), kBlock, 0, stream>>>(A);
   *rc = int(cudaGetLastError());
   return true;
 }
@@ -50,9 +54,11 @@ bool launch_sys(int S, int I, unsigned long long am, unsigned bm, unsigned long 
 }
 }  // namespace
 
-// Bytes of ring the kernel needs per trajectory for (N, I, capacity).
+// Doubles of ring the kernel needs per trajectory for (N, I, capacity); records are
+// padded to an even number of doubles (16-byte cp.async chunks).
 size_t dde_fixed_ring_doubles(int n_state, int I, int capacity) {
-  return size_t(capacity) * size_t(1 + n_state * I);
+  const int F = 1 + n_state * I;
+  return size_t(capacity) * size_t(F + (F & 1));
 }
 
 // returns 0 = launched, >0 = CUDA error code, -1 = no compiled kernel
@@ -94,6 +100,9 @@ int run_dde_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t
   A.t1 = t1;
   A.h = h;
   A.max_delay = max_delay;
+  A.hc_min = A.hc[rk.S > 1 ? 1 : 0];
+  for (int i = 1; i < rk.S; ++i)
+    if (A.hc[i] < A.hc_min) A.hc_min = A.hc[i];
   A.history_id = history_id;
   A.ring_capacity = ring_capacity;
   A.n_traj = n;

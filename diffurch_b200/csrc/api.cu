@@ -164,7 +164,8 @@ struct dfb_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t stream = nullptr;
   unsigned launches = 0;
-  int locate_batch = 12;
+  int locate_batch = 32;     // lanes parked on a detected event before the warp runs its bisections
+  int locate_max_wait = 16;  // ... or step rounds the first parked lane has waited (DFB_LOCATE_WAIT)
   bool used_hot_path = false;
 };
 
@@ -252,6 +253,7 @@ int launch_general(dfb_handle* h, const DevProblem& P, cudaStream_t stream) {
   cfg.stream = stream;
   cfg.block = 128;
   cfg.grid = int((h->n + cfg.block - 1) / cfg.block);
+  cfg.locate_max_wait = h->locate_max_wait;
   const bool has_loc = P.n_loc > 0;
   const bool fast = h->prob.arith == DFB_ARITH_FAST;
   typedef int (*Fn)(const DevProblem&, int, bool, const LaunchCfg&, int);
@@ -344,6 +346,7 @@ int dfb_create(const dfb_problem* desc, size_t n_traj, int device, dfb_handle** 
   h->n = n_traj;
   h->device = device;
   if (const char* e = std::getenv("DFB_LOCATE_BATCH")) h->locate_batch = std::atoi(e) > 0 ? std::atoi(e) : 1;
+  if (const char* e = std::getenv("DFB_LOCATE_WAIT")) h->locate_max_wait = std::atoi(e) >= 0 ? std::atoi(e) : 0;
   for (int l = 0; l < desc->n_loc; ++l)
     if (desc->loc[l].kind == DFB_LOC_PROPAGATION) h->uses_disco = true;
   if (desc->n_disco > 0) h->uses_disco = true;

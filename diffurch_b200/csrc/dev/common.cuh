@@ -75,4 +75,5 @@ struct LaunchCfg {
   cudaStream_t stream;
   int block;
   int grid;
+  int locate_max_wait;  // step rounds a parked lane may wait for its warp's event batch
 };

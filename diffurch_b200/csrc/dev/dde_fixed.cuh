@@ -53,65 +53,6 @@ struct DdeFixedArgs {
   double* ring;  // [cap][ceil(n/32)][1 + N*I][32]
 };
 
-template <int N, int I>
-struct CoeffRec {
-  double t;
-  double y[N];
-  double d[I > 1 ? I - 1 : 1][N];
-};
-
-template <int N, int I>
-struct WindowData {
-  CoeffRec<N, I> r0, r1;
-  double t_init, t_commit;  // t_commit = latest committed time (lookups at or after it are "not yet computed")
-  double t_oldest;          // t_deque[0] of the reference after its prune (lookups before it are "deleted")
-  double y0[N];
-  double hist_k;
-  int history_id;
-  uint32_t status;
-};
-
-// Horner evaluation of one record at offset s = t - t_r.
-template <int D, int N, int I>
-__device__ __forceinline__ void eval_rec(const CoeffRec<N, I>& r, double s, double* out) {
-#pragma unroll
-  for (int n = 0; n < N; ++n) {
-    if (D == 0) {
-      double acc = r.d[I - 2][n];
-#pragma unroll
-      for (int j = I - 3; j >= 0; --j) acc = fma(acc, s, r.d[j][n]);
-      out[n] = fma(acc, s, r.y[n]);
-    } else {
-      double acc = double(I - 1) * r.d[I - 2][n];
-#pragma unroll
-      for (int j = I - 3; j >= 0; --j) acc = fma(acc, s, double(j + 1) * r.d[j][n]);
-      out[n] = acc;
-    }
-  }
-}
-
-// The two-record window as the `history` of a StateRef.  STEADY = every lookup of
-// the step is known to fall after t_init and inside the retained window (checked once
-// per step by the stepper), so a lookup is a compare, a subtract and a Horner chain.
-template <int N, int I, bool STEADY>
-struct WindowHist {
-  WindowData<N, I>* w;
-  template <int D>
-  __device__ __forceinline__ void eval(double tt, double* out) {
-    if (!STEADY) {
-      if (tt <= w->t_init) {  // state.rs:162-163
-        init_condition_eval<D, N>(w->history_id, tt, w->y0, w->hist_k, w->status, out);
-        return;
-      }
-      if (tt >= w->t_commit) w->status |= DFB_TRAJ_HISTORY_NOT_READY;  // state.rs:172-177 (delay <= h)
-      if (tt < w->t_oldest) w->status |= DFB_TRAJ_HISTORY_DELETED;     // state.rs:166-171 (max_delay < delay)
-    }
-    // the branch is warp-uniform for a shared time grid and a shared delay
-    if (tt >= w->r1.t) eval_rec<D, N, I>(w->r1, tt - w->r1.t, out);
-    else eval_rec<D, N, I>(w->r0, tt - w->r0.t, out);
-  }
-};
-
 // ---- cp.async (LDGSTS) helpers: global -> shared without staging registers; completion is
 // tracked by async groups, so an in-flight prefetch never blocks unrelated instructions.
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -126,17 +67,69 @@ __device__ __forceinline__ void cp_async_wait() {
 
 constexpr int kDdeSmemSlots = 4;  // records w .. w+2 of the window plus one being overwritten
 
+// Horner evaluation of one staged record; p = this lane's column of the record block
+// [field][32] in shared memory, s = t - t_r.
+template <int D, int N, int I>
+__device__ __forceinline__ void eval_staged(const double* p, double s, double* out) {
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    if (D == 0) {
+      double acc = p[32 * (1 + N * (I - 1) + n)];
+#pragma unroll
+      for (int j = I - 2; j >= 1; --j) acc = fma(acc, s, p[32 * (1 + N * j + n)]);
+      out[n] = fma(acc, s, p[32 * (1 + n)]);
+    } else {
+      double acc = double(I - 1) * p[32 * (1 + N * (I - 1) + n)];
+#pragma unroll
+      for (int j = I - 2; j >= 1; --j) acc = fma(acc, s, double(j) * p[32 * (1 + N * j + n)]);
+      out[n] = acc;
+    }
+  }
+}
+
+// The two-record window as the `history` of a StateRef.  STEADY = every lookup of the
+// step is known to fall after t_init and inside the retained window (checked once per
+// step by the stepper), so a lookup is a compare, a subtract and a Horner chain over
+// coefficients read from the staged copy.
+template <class Stepper, bool STEADY>
+struct WindowHist {
+  Stepper* st;
+  template <int D>
+  __device__ __forceinline__ void eval(double tt, double* out) {
+    constexpr int N = Stepper::N, I = Stepper::I_;
+    if (!STEADY) {
+      if (tt <= st->A.t0) {  // state.rs:162-163: the history function (cold: state reloaded from HBM)
+        double y0[N];
+#pragma unroll
+        for (int n = 0; n < N; ++n) y0[n] = st->A.y0[size_t(n) * st->A.n_traj + st->gid];
+        const double hk = Stepper::SysT::NP >= 4 ? st->A.params[size_t(3) * st->A.n_traj + st->gid] : 0.0;
+        init_condition_eval<D, N>(st->A.history_id, tt, y0, hk, st->status, out);
+        return;
+      }
+      // the last committed time is the start of the step in flight
+      if (tt >= st->t_prev) st->status |= DFB_TRAJ_HISTORY_NOT_READY;  // state.rs:172-177 (delay <= h)
+      if (tt < st->t_oldest) st->status |= DFB_TRAJ_HISTORY_DELETED;   // state.rs:166-171 (max_delay < delay)
+    }
+    const bool second = tt >= st->tw1;
+    const double* p = second ? st->p1 : st->p0;
+    eval_staged<D, N, I>(p, tt - (second ? st->tw1 : st->tw0), out);
+  }
+};
+
 template <class Sys, int S, int I, unsigned long long AMASK, unsigned BMASK, unsigned long long BIMASK>
 struct DdeFixedStepper {
+  using SysT = Sys;
+  using Self = DdeFixedStepper;
   static constexpr int N = Sys::N;
+  static constexpr int I_ = I;
   static constexpr int NP = Sys::NP > 0 ? Sys::NP : 1;
-  static constexpr int F = 1 + N * I;     // doubles per record
-  static constexpr int FP = F + (F & 1);  // padded to an even count: 16-byte cp.async chunks
+  static constexpr int F = 1 + N * I;       // doubles per record
+  static constexpr int FP = F + (F & 1);    // padded to an even count: 16-byte cp.async chunks
   static constexpr int kWarpRec = FP * 32;  // doubles of one warp's record block
-  using Rec = CoeffRec<N, I>;
 
   const DdeFixedArgs& A;
   size_t gid;
+  size_t g_thread;  // global thread index (= trajectory index for valid lanes)
   bool valid;
   int lane;
   double* sm;  // this warp's staging area [kDdeSmemSlots][FP][32]
@@ -144,23 +137,24 @@ struct DdeFixedStepper {
   double p_curr[N], p_prev[N], d_curr[N];
   double k[S][N];
   double prm[NP];
-  WindowData<N, I> win;
-  double t_old1;       // t_deque[1] of the reference (successor of win.t_oldest on the shared time grid)
-  double tw1;          // start time of record w+1, regenerated as t_{r+1} = t_r + h (bit-exact grid replay)
-  int w;               // interval index held in win.r0
-  int fetched;         // highest record whose copy into shared memory has been issued
+  // window: records w (start tw0) and w+1 (start tw1); start times are regenerated as
+  // t_{r+1} = t_r + h, which replays the shared time grid bit for bit
+  double tw0, tw1;
+  const double *p0, *p1;  // this lane's column of the two staged records
+  double t_oldest;        // t_deque[0] of the reference after its prune
+  double t_old1;          // its successor on the grid (t_deque[1])
+  int w;
+  uint32_t status;
   bool loaded, uniform;
   unsigned warp_base, slot_stride;  // ring addressing in doubles: [slot][warp][FP][32] (host guarantees < 2^32)
 
-  size_t g_thread;     // global thread index (= trajectory index for valid lanes)
-
   __device__ DdeFixedStepper(const DdeFixedArgs& A_, size_t g_, size_t gid_, bool valid_, double* sm_)
-      : A(A_), gid(gid_), valid(valid_), lane(int(threadIdx.x & 31)), sm(sm_), g_thread(g_) {}
+      : A(A_), gid(gid_), g_thread(g_), valid(valid_), lane(int(threadIdx.x & 31)), sm(sm_) {}
 
   template <bool STEADY>
   __device__ __forceinline__ void rhs(double* out) {
-    WindowHist<N, I, STEADY> h{&win};
-    Sys::rhs(StateRef<N, WindowHist<N, I, STEADY>>{t_curr, p_curr, d_curr, t_prev, p_prev, &h}, prm, out);
+    WindowHist<Self, STEADY> h{this};
+    Sys::rhs(StateRef<N, WindowHist<Self, STEADY>>{t_curr, p_curr, d_curr, t_prev, p_prev, &h}, prm, out);
   }
 
   __device__ __forceinline__ static bool amask(int i, int j) { return (AMASK >> (i * 8 + j)) & 1ull; }
@@ -216,8 +210,8 @@ struct DdeFixedStepper {
 
   // ---- ring I/O: [slot][warp][field][lane] -----------------------------------
   // One warp's record is a contiguous FP x 256-byte block: every field access is one
-  // fully coalesced row, field offsets are compile-time immediates, and the block can
-  // be moved to shared memory with FP/2 16-byte cp.async per lane.
+  // fully coalesced row, field offsets are compile-time immediates, and the block moves
+  // to shared memory with FP/2 16-byte cp.async per lane.
   __device__ __forceinline__ double* warp_block(int rec) const {
     const unsigned slot = unsigned(rec) & unsigned(A.ring_capacity - 1);
     return A.ring + (slot * slot_stride + warp_base);
@@ -225,34 +219,18 @@ struct DdeFixedStepper {
   __device__ __forceinline__ double* smem_block(int rec) const {
     return sm + (unsigned(rec) & unsigned(kDdeSmemSlots - 1)) * unsigned(kWarpRec);
   }
-  template <class P>
-  __device__ __forceinline__ static Rec read_rec(const P* p) {  // p = block base + lane
-    Rec r;
-    r.t = p[0];
-#pragma unroll
-    for (int n = 0; n < N; ++n) r.y[n] = p[32 * (1 + n)];
-#pragma unroll
-    for (int j = 0; j < I - 1; ++j)
-#pragma unroll
-      for (int n = 0; n < N; ++n) r.d[j][n] = p[32 * (1 + N * (j + 1) + n)];
-    return r;
-  }
-  __device__ __forceinline__ static Rec inf_rec() {
-    Rec r;
-    r.t = __longlong_as_double(0x7ff0000000000000LL);
-#pragma unroll
-    for (int n = 0; n < N; ++n) {
-      r.y[n] = 0.0;
-#pragma unroll
-      for (int j = 0; j < I - 1; ++j) r.d[j][n] = 0.0;
-    }
-    return r;
-  }
   __device__ __forceinline__ void issue_fetch(int rec) {
     const double* g = warp_block(rec);
     double* d = smem_block(rec);
 #pragma unroll
     for (int q = 0; q < FP / 2; ++q) cp_async16(d + 2 * (lane + 32 * q), g + 2 * (lane + 32 * q));
+  }
+  // per-lane copy of one record (lanes of the warp disagree on the window position)
+  __device__ __forceinline__ void copy_own_column(int rec) {
+    const double* g = warp_block(rec) + lane;
+    double* d = smem_block(rec) + lane;
+#pragma unroll
+    for (int f = 0; f < F; ++f) d[32 * f] = __ldcs(g + 32 * f);
   }
 
   // commit_step (state.rs:122-139): pre-combine the interpolant of the step just
@@ -285,46 +263,54 @@ struct DdeFixedStepper {
   }
 
   // After committing record s: replay the reference's prune, slide the window so that
-  // (r0, r1) bracket the delayed times of the NEXT step, and prefetch one record ahead.
+  // records (w, w+1) bracket the delayed times of the NEXT step, and prefetch one ahead.
+  // Invariant of the staged path: after refill(s) every record <= min(w + 2, s) has been
+  // issued to shared memory, the newest of them possibly still in flight.
   __device__ __forceinline__ void refill(int s, double tau, double h) {
-    win.t_commit = t_curr;
     // prune rule of commit_step (state.rs:126-133) replayed on the shared time grid:
-    // pop while t_deque[1] < t_prev - max_delay.  t_{r+1} = t_r + h reproduces the grid bit for bit.
+    // pop while t_deque[1] < t_prev - max_delay
     const double t_tail = t_prev - A.max_delay;
     while (t_old1 < t_tail && t_old1 < t_prev) {
-      win.t_oldest = t_old1;
+      t_oldest = t_old1;
       t_old1 = t_old1 + h;
     }
+    int issued_before;  // highest record issued by earlier refills
     if (!loaded) {
       if (!(t_curr + h - tau > A.t0)) return;  // every lookup of the next step is in the history function
       loaded = true;
       w = 0;
+      tw0 = A.t0;
       tw1 = A.t0 + h;
+      issued_before = -1;
+    } else {
+      issued_before = (w + 2 < s - 1) ? w + 2 : s - 1;
     }
     const double tt_min = t_curr - tau;  // earliest delayed time of the next step (c_0 = 0)
-    while (tw1 <= tt_min) {  // record w+1 starts at or before it: slide
+    while (tw1 <= tt_min) {              // record w+1 starts at or before it: slide
       ++w;
+      tw0 = tw1;
       tw1 = tw1 + h;
     }
     if (uniform) {
-      // stage records up to w+2 (those that exist) in shared memory; the newest one
-      // issued here is not needed before the step after next
       const int want = (w + 2 < s) ? w + 2 : s;
-      const int fetched_before = fetched;
+      // a 16-byte chunk holds the columns of two lanes: when the record just committed is
+      // fetched straight back (short delays), the other lanes' stores must be ordered first
+      if (want >= s) __syncwarp();
 #pragma unroll 1
-      while (fetched < want) issue_fetch(++fetched);
+      for (int r = issued_before + 1; r <= want; ++r) issue_fetch(r);
       cp_async_commit();
-      const int need = (w + 1 < s) ? w + 1 : s;  // newest record the next step reads
-      if (need <= fetched_before) cp_async_wait<1>();   // issued in an earlier refill
-      else cp_async_wait<0>();                           // start-up / short delays: issued just now
+      const int need = (w + 1 < s) ? w + 1 : s;        // newest record the next step reads
+      if (need <= issued_before) cp_async_wait<1>();   // issued by an earlier refill: one step of slack
+      else cp_async_wait<0>();                         // start-up / short delays: issued just now
       __syncwarp();
-      win.r0 = read_rec(smem_block(w) + lane);
-      win.r1 = (w + 1 <= s) ? read_rec(smem_block(w + 1) + lane) : inf_rec();
     } else {
-      // lanes of this warp have different delays: per-lane records straight from HBM
-      win.r0 = read_rec(warp_block(w) + lane);
-      win.r1 = (w + 1 <= s) ? read_rec(warp_block(w + 1) + lane) : inf_rec();
+      copy_own_column(w);
+      if (w + 1 <= s) copy_own_column(w + 1);
     }
+    p0 = smem_block(w) + lane;
+    p1 = smem_block(w + 1) + lane;
+    // If record w+1 is the step about to be taken (short delays) its start time tw1 equals the
+    // next step's t_prev, so only lookups the reference rejects as "not yet computed" select it.
   }
 
   __device__ void run() {
@@ -338,30 +324,27 @@ struct DdeFixedStepper {
     const size_t n_warps = (n_traj + 31) / 32;
     slot_stride = unsigned(n_warps * size_t(kWarpRec));
     warp_base = unsigned((g_thread / 32) * size_t(kWarpRec));
-    win.t_init = A.t0;
-    win.t_commit = A.t0;
-    win.t_oldest = A.t0;
-    t_old1 = A.t0 + A.h;
-    tw1 = A.t0 + A.h;
-    win.history_id = A.history_id;
-    win.hist_k = Sys::NP >= 4 ? prm[Sys::NP >= 4 ? 3 : 0] : 0.0;
-    win.status = 0u;
-#pragma unroll
-    for (int n = 0; n < N; ++n) win.y0[n] = A.y0[size_t(n) * n_traj + gid];
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    win.r0 = inf_rec();
-    win.r1 = inf_rec();
+    t_oldest = A.t0;
+    t_old1 = A.t0 + A.h;
+    tw0 = tw1 = inf;
+    p0 = p1 = sm + lane;
+    status = 0u;
     loaded = false;
     w = 0;
-    fetched = -1;
     // State::new (state.rs:52-81)
     t_curr = t_prev = A.t0;
-    double p0[N];
-    init_condition_eval<0, N>(A.history_id, A.t0, win.y0, win.hist_k, win.status, p0);
+    {
+      double y0[N], p0v[N];
 #pragma unroll
-    for (int n = 0; n < N; ++n) {
-      p_curr[n] = p_prev[n] = p0[n];
-      d_curr[n] = 0.0;
+      for (int n = 0; n < N; ++n) y0[n] = A.y0[size_t(n) * n_traj + gid];
+      const double hk = Sys::NP >= 4 ? prm[Sys::NP >= 4 ? 3 : 0] : 0.0;
+      init_condition_eval<0, N>(A.history_id, A.t0, y0, hk, status, p0v);
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        p_curr[n] = p_prev[n] = p0v[n];
+        d_curr[n] = 0.0;
+      }
     }
     int s = 0;  // index of the step being taken = ring record it will write
     // A trajectory that hits one of the reference's panics keeps stepping (its warp must
@@ -369,12 +352,11 @@ struct DdeFixedStepper {
     if (t_curr < A.t1) {
       rhs<false>(d_curr);  // k[0] of the first step (state.rs:97-98)
       const double h = A.h;
-      // Phase A: some lookup of the step may still reach the history function, or
-      // the window is not in its steady state: every lookup carries the checks.
+      // Phase A: some lookup of the step may still reach the history function, or the
+      // delay does not exceed the step: every lookup carries the reference's checks.
 #pragma unroll 1
       while (t_curr < A.t1 && (A.t1 - t_curr) >= h &&
-             !(loaded && (t_curr - tau) > A.t0 && (t_curr - tau) >= win.r0.t &&
-               (t_curr + h) - tau < t_curr)) {
+             !(loaded && (t_curr - tau) > A.t0 && (t_curr - tau) >= tw0 && (t_curr + h) - tau < t_curr)) {
         step<true, false>(h);
         commit<true>(s, h);
         refill(s, tau, h);
@@ -386,7 +368,7 @@ struct DdeFixedStepper {
       // (state.rs:166-171).
 #pragma unroll 1
       while (t_curr < A.t1 && (A.t1 - t_curr) >= h) {
-        if ((t_curr + A.hc_min) - tau < win.t_oldest) win.status |= DFB_TRAJ_HISTORY_DELETED;
+        if ((t_curr + A.hc_min) - tau < t_oldest) status |= DFB_TRAJ_HISTORY_DELETED;
         step<true, true>(h);
         commit<true>(s, h);
         refill(s, tau, h);
@@ -407,7 +389,6 @@ struct DdeFixedStepper {
     bool finite = true;
 #pragma unroll
     for (int n = 0; n < N; ++n) finite = finite && (fabs(p_curr[n]) < inf);
-    uint32_t status = win.status;
     if (!finite && status == 0u) status |= DFB_TRAJ_NONFINITE;
     A.t_final[gid] = t_curr;
 #pragma unroll

@@ -636,7 +636,7 @@ struct Integrator {
   // ---- Solver::run (solver.rs:275-313) as a warp-friendly state machine -----
   // `valid` = this lane owns a trajectory.  All 32 lanes stay in the loop so
   // the warp votes are full-mask.
-  __device__ void run(bool valid, int locate_batch_threshold) {
+  __device__ void run(bool valid, int locate_batch_threshold, int locate_max_wait) {
     int mode = MODE_DONE;
     if (valid) {
       init();
@@ -647,6 +647,7 @@ struct Integrator {
     int ev_index = 0;
     uint32_t fired_mask = 0u;  // locators that detected on the parked step
     const bool adaptive = P.stepsize_kind == DFB_STEP_AUTOMATIC;
+    int parked_iters = 0;  // warp-uniform: step rounds since the first lane parked
 
     while (true) {
       const unsigned stepping =
@@ -654,9 +655,13 @@ struct Integrator {
       const unsigned parked = HAS_LOC ? __ballot_sync(0xffffffffu, mode == MODE_LOCATE) : 0u;
       if (stepping == 0u && parked == 0u) break;
 
-      // (1) batched event location for the parked lanes
+      // (1) batched event location for the parked lanes: run the bisections once enough
+      // lanes are parked, or the first parked lane has waited `locate_max_wait` step
+      // rounds (bounds the idle time when events are rare), or nobody else can advance.
       if (HAS_LOC && parked != 0u &&
-          (stepping == 0u || __popc(parked) >= locate_batch_threshold)) {
+          (stepping == 0u || __popc(parked) >= locate_batch_threshold ||
+           parked_iters >= locate_max_wait)) {
+        parked_iters = 0;
         if (mode == MODE_LOCATE) {
           // HListLocateEarliest (loc.rs:821-835): strictly earliest, first index wins ties
           bool found = false;
@@ -687,6 +692,8 @@ struct Integrator {
         }
         continue;
       }
+
+      if (HAS_LOC && parked != 0u) ++parked_iters;
 
       // (2) one make_step for every lane that can advance
       if (mode == MODE_STEP || mode == MODE_EVENT_RESTEP) {
@@ -740,11 +747,12 @@ struct Integrator {
 
 template <class Sys, int S, int I, bool HAS_LOC>
 __global__ void __launch_bounds__(128)
-    integrate_general_kernel(const __grid_constant__ DevProblem P, int locate_batch_threshold) {
+    integrate_general_kernel(const __grid_constant__ DevProblem P, int locate_batch_threshold,
+                             int locate_max_wait) {
   const size_t gid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool valid = gid < P.n_traj;
   Integrator<Sys, S, I, HAS_LOC> it(P, valid ? gid : 0);
-  it.run(valid, locate_batch_threshold);
+  it.run(valid, locate_batch_threshold, locate_max_wait);
 }
 
 }  // namespace DFB_NS

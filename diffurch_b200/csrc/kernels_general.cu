@@ -12,10 +12,11 @@ namespace DFB_NS {
 namespace {
 template <class Sys, int S, int I>
 int launch_one(const DevProblem& P, bool has_loc, const LaunchCfg& c, int thr) {
+  const int wait = c.locate_max_wait;
   if (has_loc)
-    integrate_general_kernel<Sys, S, I, true><<<c.grid, c.block, 0, c.stream>>>(P, thr);
+    integrate_general_kernel<Sys, S, I, true><<<c.grid, c.block, 0, c.stream>>>(P, thr, wait);
   else
-    integrate_general_kernel<Sys, S, I, false><<<c.grid, c.block, 0, c.stream>>>(P, thr);
+    integrate_general_kernel<Sys, S, I, false><<<c.grid, c.block, 0, c.stream>>>(P, thr, wait);
   return int(cudaGetLastError());
 }
 }  // namespace

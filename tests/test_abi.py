@@ -68,6 +68,10 @@ def test_invalid_descriptors_are_rejected_without_gpu():
     p.loc[0].detector_id = 3  # Lorenz registers no detector
     assert d.lib.dfb_create(C.byref(p), 4, 0, C.byref(h)) == abi.ERR_INVALID
     assert b"detector" in d.lib.dfb_last_error()
+    # empty ensemble
+    p = d.default_problem()
+    p.system_id = abi.SYS_LORENZ
+    assert d.lib.dfb_create(C.byref(p), 0, 0, C.byref(h)) == abi.ERR_INVALID
     # generic_order_3 with arguments the reference panics on (rk.rs:200)
     with pytest.raises(d.DfbError):
         d.RK.generic_order_3(2.0 / 3.0, 0.5)

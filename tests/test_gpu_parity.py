@@ -179,16 +179,19 @@ def test_bouncing_ball_strict_bit_exact(oracle):
 
 
 def test_bouncing_ball_batching_threshold_does_not_change_results():
-    res = []
-    for thr in ("1", "8", "32"):
-        os.environ["DFB_LOCATE_BATCH"] = thr
-        try:
-            res.append(cases.bouncing_ball(n=200, t1=6.0).run())
-        finally:
-            del os.environ["DFB_LOCATE_BATCH"]
-    for r in res[1:]:
-        assert np.array_equal(r.p, res[0].p) and np.array_equal(r.event_t, res[0].event_t)
-        assert np.array_equal(r.steps, res[0].steps)
+    # warp-level event batching is a scheduling decision only: per-trajectory results must
+    # not depend on the batch threshold or on the bounded wait
+    for mk in (lambda: cases.bouncing_ball(n=200, t1=6.0), lambda: cases.egg_billiard(n=100, reflections=40)):
+        res = []
+        for thr, wait in (("1", "0"), ("8", "4"), ("32", "16"), ("32", "100000")):
+            os.environ["DFB_LOCATE_BATCH"], os.environ["DFB_LOCATE_WAIT"] = thr, wait
+            try:
+                res.append(mk().run())
+            finally:
+                del os.environ["DFB_LOCATE_BATCH"], os.environ["DFB_LOCATE_WAIT"]
+        for r in res[1:]:
+            assert np.array_equal(r.p, res[0].p) and np.array_equal(r.event_t, res[0].event_t)
+            assert np.array_equal(r.steps, res[0].steps) and np.array_equal(r.events, res[0].events)
 
 
 def test_bouncing_ball_fast_event_times_within_tolerance(oracle):

@@ -1,0 +1,93 @@
+"""Two-GPU checks (skipped on a one-GPU box): the ensemble shards by trajectory range, each
+rank integrates its shard on its own GPU, and the final states are gathered over NCCL —
+once through torch.distributed and once through the C-ABI `dfb_gather_final`
+(ncclAllGather on the library's own packed buffers)."""
+import ctypes as C
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count() if torch.cuda.is_available() else 0
+    except Exception:
+        return 0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, out_path):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import diffurch_b200 as d
+    from diffurch_b200 import distributed as dd
+
+    rho = 20.0 + 20.0 * np.arange(n) / (n - 1)
+    prm = np.stack([np.full(n, 10.0), rho, np.full(n, 8.0 / 3.0)], axis=1)
+    y0 = np.tile([1.0, 2.0, 20.0], (n, 1))
+
+    def make(y0s, prms):
+        return (d.Solver.new(device=rank).initial(y0s).equation(d.systems.Lorenz, prms)
+                .interval(0.0, 2.0).stepsize(1.0 / 250.0))
+
+    # (1) torch.distributed gather of ragged shards
+    got = dd.run_sharded(make, y0, prm, rank, world, device=f"cuda:{rank}")
+
+    # (2) C-ABI ncclAllGather (equal shards): raw ncclComm_t from torch's bundled NCCL
+    m = n // world
+    lo = rank * m
+    ens = make(y0[lo:lo + m], prm[lo:lo + m]).build()
+    ens.run()
+    uid = [torch.cuda.nccl.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    capsule = torch._C._nccl_init_rank(world, uid[0], rank)
+    C.pythonapi.PyCapsule_GetName.restype = C.c_char_p
+    C.pythonapi.PyCapsule_GetName.argtypes = [C.py_object]
+    C.pythonapi.PyCapsule_GetPointer.restype = C.c_void_p
+    C.pythonapi.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
+    comm = C.pythonapi.PyCapsule_GetPointer(capsule, C.pythonapi.PyCapsule_GetName(capsule))
+    t_all = np.empty(m * world)
+    y_all = np.empty((m * world, 3))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    rc = d.lib.dfb_gather_final(ens._h, C.c_void_p(comm), world, dp(t_all), dp(y_all), None)
+    assert rc == 0, d.lib.dfb_last_error()
+    if rank == 0:
+        np.savez(out_path, p=got["p"], t=got["t"], y_all=y_all, t_all=t_all)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_run_and_nccl_gather(tmp_path):
+    import torch.multiprocessing as mp
+    import diffurch_b200 as d
+    n = 2050  # ragged for the torch path: 1025 + 1025; the C-ABI leg uses 2 x 1025
+    out = str(tmp_path / "g.npz")
+    mp.spawn(_worker, args=(2, _free_port(), n, out), nprocs=2, join=True)
+    got = np.load(out)
+    rho = 20.0 + 20.0 * np.arange(n) / (n - 1)
+    prm = np.stack([np.full(n, 10.0), rho, np.full(n, 8.0 / 3.0)], axis=1)
+    one = (d.Solver.new().initial(np.tile([1., 2., 20.], (n, 1))).equation(d.systems.Lorenz, prm)
+           .interval(0.0, 2.0).stepsize(1.0 / 250.0).run())
+    assert np.array_equal(got["p"], one.p) and np.array_equal(got["t"], one.t)
+    assert np.array_equal(got["y_all"], one.p) and np.array_equal(got["t_all"], one.t)

@@ -1,0 +1,70 @@
+#!/usr/bin/env python3
+"""Throughput of the non-headline BASELINE configs (events, Lyapunov batch, adaptive,
+strict arithmetic) on one GPU.  Prints one JSON object; used for profiles/, not by the driver."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import cases  # noqa: E402
+import diffurch_b200 as d  # noqa: E402
+
+
+def timed(make, reps=2):
+    ens = make().build()
+    ens.run()
+    ens.synchronize()
+    ms = []
+    for _ in range(reps):
+        ens.run()
+        ens.synchronize()
+        ms.append(ens.totals()["kernel_ms"])
+    tot = ens.totals()
+    ens.close()
+    ms = float(np.mean(ms))
+    return {"kernel_ms": ms, "steps": tot["steps"], "events": tot["events"], "rejected": tot["rejected"],
+            "rhs_evals": tot["rhs_evals"], "n_failed": tot["n_failed"],
+            "steps_per_s": tot["steps"] / (ms * 1e-3), "events_per_s": tot["events"] / (ms * 1e-3)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the BASELINE ensemble sizes")
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    out = {}
+    n_ev = int((1 << 19) * args.scale)
+    n_ly = int((1 << 16) * args.scale)
+    n_lo = int((1 << 20) * args.scale)
+    todo = {
+        "bouncing_ball_2^19_t8_fast": lambda: cases.bouncing_ball(n=n_ev, t1=8.0, arith="fast", events=0),
+        "bouncing_ball_2^19_t8_strict": lambda: cases.bouncing_ball(n=n_ev, t1=8.0, arith="strict", events=0),
+        "egg_billiard_2^19_200refl_fast": lambda: cases.egg_billiard(n=n_ev, reflections=200, arith="fast", events=0),
+        "lyapunov_lorenz_2^16_rho_grid_t100_fast": lambda: cases.lyap_lorenz(100.0, rho=np.linspace(20.0, 40.0, n_ly), arith="fast"),
+        "lorenz_2^20_adaptive_fast": lambda: cases.lorenz(n=n_lo, t1=50.0, arith="fast").stepsize(
+            d.AutomaticStepsize(1e-2, (1e-6, 1e-1), [1e-9] * 3, [1e-9] * 3, 4, 0.9, (0.2, 5.0))),
+        "lorenz_2^20_rk4_fast": lambda: cases.lorenz(n=n_lo, t1=50.0, arith="fast", rk=d.RK.rk4()),
+        "lorenz_2^20_rktp64_strict": lambda: cases.lorenz(n=n_lo, t1=50.0, arith="strict"),
+    }
+    for name, mk in todo.items():
+        if args.only and args.only not in name:
+            continue
+        t0 = time.time()
+        try:
+            out[name] = timed(mk)
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"error": repr(e)}
+        out[name]["wall_s"] = time.time() - t0
+        print(name, json.dumps(out[name]), file=sys.stderr, flush=True)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

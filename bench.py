@@ -36,6 +36,9 @@ T_END = 50.0
 H = 1.0 / 250.0
 STEPS_PER_MEMBER = 12501  # 12500 x (1/250) accumulates to one ulp short of 50, then one closing step
 FLOPS_PER_STEP = 252.0  # Lorenz + rktp64, FMA = 2, structural zeros skipped
+# DRAM bytes of ONE launch of the headline kernel at 2^20 members (ncu --set full, profiles/r1_run3_*):
+# 52.07 MB read + 8.42 MB written
+ODE_DRAM_TRAFFIC_PER_LAUNCH = 52074752 + 8422656
 WORKLOAD = "lorenz_2^20_members_rho_sweep_rktp64_h=1/250_t=[0,50]"
 
 
@@ -116,6 +119,7 @@ def cpu_oracle_rate(n_sample, threads):
 
 
 DDE_MEMBERS = 1 << 18
+DDE_DRAM_TRAFFIC_PER_LAUNCH = 61275530000 + 62334931000  # ncu, profiles/r1_run4_ncu_full_dde_fixed.txt
 DDE_BYTES_PER_STEP = 96.0  # one 48-byte coefficient record written + read per RK step (N=1, I=5)
 
 
@@ -163,7 +167,11 @@ def dde_leg(d, torch, local_rank, K=3, W=2):
         "rk_steps_per_member": int(steps // n), "n_failed": int(tot["n_failed"]),
         "max_abs_err_vs_exact_sin": err,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                     "frac": achieved / hbm, "traffic": None, "peak_source": src,
+                     "frac": achieved / hbm, "traffic": DDE_DRAM_TRAFFIC_PER_LAUNCH,
+                     "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch, "
+                                       "profiles/r1_run4_ncu_full_dde_fixed.txt (algorithmic bytes per launch: "
+                                       f"{int(DDE_BYTES_PER_STEP * steps)})",
+                     "peak_source": src,
                      "algorithmic_bytes_per_rk_step": DDE_BYTES_PER_STEP,
                      "kernel": "dde_fixed_kernel<SysDdeLinear,7,5,rktp64-sparsity>"},
     }
@@ -200,7 +208,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--members", type=int, default=N_MEMBERS, help=argparse.SUPPRESS)
@@ -322,14 +330,27 @@ def main():
     d.lib.dfb_measure_fp64_peak(local_rank, C.byref(tf64), C.byref(mhz))
     kern_avg_ms = total_ms / K  # one launch per step; events bracket exactly that launch
     achieved_tflops = FLOPS_PER_STEP * steps_per_pass / (kern_avg_ms * 1e-3) / 1e12
+    # Denominator: MEASURED_PEAKS.json has no FP64 entry and B200_PROFILING.md states no FP64
+    # fallback, so the peak is measured here (DFMA-chain microbenchmark, best of 2 operand
+    # patterns x 2 chain counts x 4 occupancies).  The pipe's architectural rate at the clock
+    # observed during the timed region (SMs x 64 DFMA/clk x 2 x f) is reported next to it, and
+    # the LARGER of the two is the denominator, so the fraction can only be understated.
+    props = torch.cuda.get_device_properties(local_rank)
+    sm_mhz_obs = (clocks or {}).get("sm_mhz") or 1965.0
+    arch_peak = props.multi_processor_count * 64 * 2 * sm_mhz_obs * 1e6 / 1e12
+    peak = max(tf64.value, arch_peak)
     roofline = {
-        "bound": "fp64", "achieved": achieved_tflops, "peak": tf64.value, "unit": "TFLOP/s",
-        "frac": achieved_tflops / tf64.value if tf64.value > 0 else None,
-        "traffic": None,
-        "peak_source": "DFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry); "
-                       "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2",
+        "bound": "fp64", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
+        "frac": achieved_tflops / peak,
+        "traffic": ODE_DRAM_TRAFFIC_PER_LAUNCH if n == N_MEMBERS else None,
+        "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch, "
+                          "profiles/r1_run3_ncu_full_ode_fixed_lorenz.txt (algorithmic HBM bytes per launch: "
+                          f"{100 * n}; the kernel is FP64-pipe-bound, not HBM-bound)",
+        "peak_source": "max(DFMA-chain microbenchmark measured in this run, SMs x 64 DFMA/clk x 2 x SM clock "
+                       "sampled during the timed region); MEASURED_PEAKS.json has no FP64 entry",
+        "peak_measured_dfma_chain": tf64.value,
+        "peak_architectural_at_observed_clock": arch_peak,
         "peak_sm_mhz": mhz.value,
-        "frac_of_nominal_37.2": achieved_tflops / 37.2,
         "algorithmic_flops_per_rk_step": FLOPS_PER_STEP,
         "kernel": "ode_fixed_kernel<SysLorenz,7,rktp64-sparsity,FAST>",
         "kernel_ms": kern_avg_ms,
@@ -338,7 +359,9 @@ def main():
 
     # ---- CPU baseline (oracle "port"), bounded sample on this box's host cores ----
     cores = os.cpu_count() or 1
-    n_sample = 2048 * cores
+    probe_rate, _, _ = cpu_oracle_rate(256 * cores, cores)       # sizes the sample for ~12 s of CPU work
+    n_sample = int(max(1024 * cores, min(N_MEMBERS, 12.0 * probe_rate / STEPS_PER_MEMBER)))
+    n_sample -= n_sample % cores
     cpu_rate, cpu_dt, _ = cpu_oracle_rate(n_sample, cores)
     cpu1_rate, _, _ = cpu_oracle_rate(64, 1)
     cpu_baseline = {

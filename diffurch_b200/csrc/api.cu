@@ -103,7 +103,10 @@ __global__ void soa_to_aos_kernel(const double* __restrict__ src, double* __rest
 }
 
 // ---- FP64 peak microbenchmark: CHAINS independent DFMA chains per thread
-template <int CHAINS>
+// MODE 0: x = fma(x, a, b) (three distinct operands); MODE 1: x = fma(x, a, x) (the accumulator
+// is also the addend: two register operands + one constant-bank operand, no register-bank
+// conflict possible).  The launcher keeps the best rate over both.
+template <int CHAINS, int MODE>
 __global__ void __launch_bounds__(256) dfma_chain_kernel(double* out, int iters, double a, double b,
                                                          long long* cycles) {
   double x[CHAINS];
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(256) dfma_chain_kernel(double* out, int iters,
 #pragma unroll
     for (int u = 0; u < 8; ++u)
 #pragma unroll
-      for (int c = 0; c < CHAINS; ++c) x[c] = fma(x[c], a, b);
+      for (int c = 0; c < CHAINS; ++c) x[c] = MODE == 0 ? fma(x[c], a, b) : fma(x[c], a, x[c]);
   }
   const long long c1 = clock64();
   double s = 0.0;
@@ -813,14 +816,17 @@ int dfb_measure_fp64_peak(int device, double* tflops, double* sm_mhz_est) {
   double best_tf = 0.0, mhz = 0.0;
   // sweep resident blocks per SM x chains per thread; keep the best rate
   for (int per_sm = 1; per_sm <= 8; per_sm *= 2) {
-    for (int chains = 8; chains <= 16; chains *= 2) {
+    for (int variant = 0; variant < 4; ++variant) {
+      const int chains = (variant & 1) ? 16 : 8;
+      const int mode = variant >> 1;
       const int blocks = prop.multiProcessorCount * per_sm;
       float best_ms = 1e30f;
       for (int rep = 0; rep < 4; ++rep) {
         cudaEventRecord(e0);
-        if (chains == 4) dfma_chain_kernel<4><<<blocks, block>>>(d_out, iters, 0.999999, 1e-7, d_cyc);
-        else if (chains == 8) dfma_chain_kernel<8><<<blocks, block>>>(d_out, iters, 0.999999, 1e-7, d_cyc);
-        else dfma_chain_kernel<16><<<blocks, block>>>(d_out, iters, 0.999999, 1e-7, d_cyc);
+        if (mode == 0 && chains == 8) dfma_chain_kernel<8, 0><<<blocks, block>>>(d_out, iters, 0.999999, 1e-7, d_cyc);
+        else if (mode == 0) dfma_chain_kernel<16, 0><<<blocks, block>>>(d_out, iters, 0.999999, 1e-7, d_cyc);
+        else if (chains == 8) dfma_chain_kernel<8, 1><<<blocks, block>>>(d_out, iters, 1e-9, 0.0, d_cyc);
+        else dfma_chain_kernel<16, 1><<<blocks, block>>>(d_out, iters, 1e-9, 0.0, d_cyc);
         cudaEventRecord(e1);
         DFB_CUDA(cudaEventSynchronize(e1));
         float ms = 0.f;
@@ -830,7 +836,7 @@ int dfb_measure_fp64_peak(int device, double* tflops, double* sm_mhz_est) {
       const double flops = 2.0 * 8.0 * chains * double(iters) * double(block) * double(blocks);
       const double tf = flops / (double(best_ms) * 1e-3) / 1e12;
       if (tf > best_tf) best_tf = tf;
-      if (per_sm == 1 && chains == 16) {
+      if (per_sm == 1 && chains == 16 && mode == 0) {
         // one block per SM: block 0 spans the whole launch, so its cycle count / time = SM clock
         long long cyc = 0;
         DFB_CUDA(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost));

@@ -1,0 +1,282 @@
+// Hot path #1b: adaptive-step explicit RK over an ODE ensemble, no events, no delay
+// history, FAST arithmetic (reference: Solver::run solver.rs:292-310 with an
+// `AutomaticStepsize` controller, stepsize.rs:35-85; State::make_step state.rs:94-120).
+//
+// Like the fixed-step kernel every trajectory lives in registers, so the bound is the
+// FP64 pipe.  What is different is that trajectories take different numbers of steps:
+//
+//  * every lane carries its own (t, h); an attempted step is the same instruction stream
+//    for every lane whether it will be accepted or rejected, so rejections never diverge
+//    the warp (the reference's `undo_step` + new `make_step` is simply "do not commit");
+//  * lanes that finish early do not idle until the slowest lane of their warp is done:
+//    a finished lane stores its result and pulls the next trajectory index from a global
+//    work counter (dynamic trajectory assignment; results are indexed by trajectory, so
+//    they do not depend on which lane integrated what);
+//  * the controller's `(1/err).powf(1/(order+1))` — one libm `pow` per attempted step in
+//    the reference — is a MUFU-seeded Newton iteration on f^-p = err (two iterations:
+//    a few ulp), and its three divisions use a MUFU-seeded reciprocal; both fall back to
+//    the IEEE `pow` / division outside the range where the shortcut is safe, so the
+//    corner cases (err = 0, inf, NaN) behave exactly as the reference's formula does.
+//
+// Only systems whose right-hand side is a pure function of (t, p, params) may use this
+// kernel (`Sys::pure_rhs`): the reference re-evaluates k[0] after an `undo_step`
+// (state.rs:97-98), which for a pure function reproduces the value already held.
+#pragma once
+#include "common.cuh"
+#include "ode_fixed.cuh"
+#include "systems.cuh"
+
+namespace DFB_NS {
+
+struct OdeAdaptiveArgs {
+  double a[DFB_MAX_STAGES * DFB_MAX_STAGES];
+  double b[DFB_MAX_STAGES];
+  double c[DFB_MAX_STAGES];
+  double e[DFB_MAX_STAGES];  // b2_j - b_j (host-computed, one IEEE subtraction as in state.rs:118)
+  dfb_auto_stepsize ctl;
+  double t0, t1;
+  double inv_p;   // 1 / (order + 1) as the reference forms it (stepsize.rs:74)
+  float inv_pf;
+  int32_t p;      // order + 1
+  size_t n_traj;
+  const double* y0;
+  const double* params;
+  double* t_final;
+  double* y_final;
+  unsigned long long* steps;
+  unsigned long long* rejected;
+  unsigned long long* rhs_evals;
+  uint32_t* status;
+  unsigned long long* queue;  // next unassigned trajectory (zeroed before the launch)
+};
+
+// 1/x for a positive, normal x: MUFU.RCP64H seed + two Newton steps (relative error ~1e-16).
+__device__ __forceinline__ double fast_rcp_pos(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+// exponent field strictly inside (1, 2045): positive-or-negative normal number far from both ends
+__device__ __forceinline__ bool safely_normal(double x) {
+  const unsigned hi = unsigned(__double2hiint(x)) & 0x7fffffffu;
+  return (hi - 0x06400000u) < 0x73000000u;  // 2^-923 .. 2^+923
+}
+
+template <int P>
+__device__ __forceinline__ double pow_small(double f) {
+  double r = f;
+#pragma unroll
+  for (int q = 1; q < P; ++q) r *= f;
+  return r;
+}
+
+// (1/err)^(1/p)  (stepsize.rs:73-74)
+__device__ __forceinline__ double inv_root(double err, int p, double inv_p, float inv_pf) {
+  if (err > 1e-30 && err < 1e30) {
+    float lg, g;
+    const float ef = float(err);
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(ef));
+    const float x = -inv_pf * lg;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(x));
+    double f = double(g);  // ~1e-6 relative
+    const double pp1 = double(p + 1);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {  // Newton on f^-p = err: f <- f ((p+1) - err f^p) / p
+      double fp;
+      if (p == 5) {
+        const double f2 = f * f;
+        fp = f2 * f2 * f;
+      } else {
+        fp = f;
+        for (int q = 1; q < p; ++q) fp *= f;
+      }
+      f = f * fma(-err, fp, pp1) * inv_p;
+    }
+    return f;
+  }
+  return pow(1.0 / err, inv_p);
+}
+
+template <class Sys, int S, unsigned long long AMASK, unsigned BMASK, unsigned EMASK, int TPT>
+struct OdeAdaptiveStepper {
+  static constexpr int N = Sys::N;
+  static constexpr int NP = Sys::NP > 0 ? Sys::NP : 1;
+  using Ref = StateRef<N, NoHist>;
+
+  const OdeAdaptiveArgs& A;
+  size_t idx[TPT];
+  bool active[TPT];
+  double t[TPT], h_auto[TPT];
+  double p[TPT][N], d[TPT][N];
+  double prm[TPT][NP];
+  unsigned n_steps[TPT], n_rej[TPT];  // per trajectory; 2^32 attempts of one member is beyond any run
+  uint32_t flags[TPT];
+  NoHist nohist;
+
+  __device__ explicit OdeAdaptiveStepper(const OdeAdaptiveArgs& A_) : A(A_) {}
+
+  __device__ __forceinline__ void rhs(int u, double tt, const double* y, double* out) {
+    Sys::rhs(Ref{tt, y, d[u], tt, y, &nohist}, prm[u], out);
+  }
+
+  __device__ void fetch(int u) {
+    const unsigned long long i = atomicAdd(A.queue, 1ull);
+    active[u] = i < A.n_traj;
+    if (!active[u]) return;
+    idx[u] = size_t(i);
+    const size_t n_traj = A.n_traj;
+#pragma unroll
+    for (int n = 0; n < Sys::NP; ++n) prm[u][n] = A.params[size_t(n) * n_traj + i];
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      p[u][n] = A.y0[size_t(n) * n_traj + i];
+      d[u][n] = 0.0;
+    }
+    t[u] = A.t0;
+    h_auto[u] = A.ctl.stepsize;
+    n_steps[u] = n_rej[u] = 0u;
+    flags[u] = 0u;
+    if (t[u] < A.t1) rhs(u, t[u], p[u], d[u]);  // k[0] of the first make_step (state.rs:97-98)
+  }
+
+  __device__ void store(int u) {
+    const size_t n_traj = A.n_traj, i = idx[u];
+    bool finite = true;
+#pragma unroll
+    for (int n = 0; n < N; ++n) finite = finite && (fabs(p[u][n]) < __longlong_as_double(0x7ff0000000000000LL));
+    A.t_final[i] = t[u];
+#pragma unroll
+    for (int n = 0; n < N; ++n) A.y_final[size_t(n) * n_traj + i] = p[u][n];
+    const unsigned long long attempts = (unsigned long long)n_steps[u] + n_rej[u];
+    A.steps[i] = n_steps[u];
+    A.rejected[i] = n_rej[u];
+    // as the reference evaluates: S per attempt, k[0] once at the start and once after every undo
+    A.rhs_evals[i] = attempts > 0 ? attempts * S + 1 + n_rej[u] : 0;
+    A.status[i] = flags[u] | (finite ? 0u : uint32_t(DFB_TRAJ_NONFINITE));
+  }
+
+  // one attempted step for every slot (make_step + StepsizeController::update + commit/undo)
+  __device__ __forceinline__ void attempt() {
+    double hs[TPT];
+    double k[TPT][S][N];
+    double y[TPT][N];
+#pragma unroll
+    for (int u = 0; u < TPT; ++u) {
+      hs[u] = fmin(h_auto[u], A.t1 - t[u]);  // solver.rs:293
+#pragma unroll
+      for (int n = 0; n < N; ++n) k[u][0][n] = d[u][n];
+    }
+#pragma unroll
+    for (int i = 1; i < S; ++i) {
+#pragma unroll
+      for (int u = 0; u < TPT; ++u) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+          double acc = 0.0;
+          bool first = true;
+#pragma unroll
+          for (int j = 0; j < i; ++j)
+            if (AMASK & amask_bit(i, j)) {
+              acc = first ? k[u][j][n] * A.a[i * DFB_MAX_STAGES + j]
+                          : fma(k[u][j][n], A.a[i * DFB_MAX_STAGES + j], acc);
+              first = false;
+            }
+          y[u][n] = fma(acc, hs[u], p[u][n]);
+        }
+        rhs(u, fma(A.c[i], hs[u], t[u]), y[u], k[u][i]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < TPT; ++u) {
+      double err = 0.0;
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        double acc = 0.0, ea = 0.0;
+        bool first = true, efirst = true;
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+          if (BMASK & (1u << j)) {
+            acc = first ? k[u][j][n] * A.b[j] : fma(k[u][j][n], A.b[j], acc);
+            first = false;
+          }
+          if (EMASK & (1u << j)) {
+            ea = efirst ? k[u][j][n] * A.e[j] : fma(k[u][j][n], A.e[j], ea);
+            efirst = false;
+          }
+        }
+        y[u][n] = fma(acc, hs[u], p[u][n]);
+        // AutomaticStepsize::update (stepsize.rs:65-71): |e| / (atol + |e| rtol), max over components
+        const double ae = fabs(ea * hs[u]);
+        const double den = fma(ae, A.ctl.rtol[n], A.ctl.atol[n]);
+        const double q = safely_normal(den) ? ae * fast_rcp_pos(den) : ae / den;
+        err = n == 0 ? q : fmax(err, q);
+      }
+      const double t_new = t[u] + hs[u];
+      double d_new[N];
+      rhs(u, t_new, y[u], d_new);
+      double factor = A.ctl.fac * inv_root(err, A.p, A.inv_p, A.inv_pf);
+      factor = dev_clamp(factor, A.ctl.fac_min, A.ctl.fac_max);
+      double h_next = h_auto[u] * factor;
+      h_next = dev_clamp(h_next, A.ctl.stepsize_min, A.ctl.stepsize_max);
+      const bool rejected = err >= 1.0;
+      if (active[u]) {
+        h_auto[u] = h_next;
+        if (rejected) {
+          ++n_rej[u];
+          // The same step from the same state gives the same error: the reference would spin
+          // forever here (solver.rs:294-297).  Stop the trajectory and say so.
+          if (fmin(h_next, A.t1 - t[u]) == hs[u]) {
+            flags[u] |= DFB_TRAJ_STEPSIZE_FLOOR;
+            t[u] = __longlong_as_double(0x7ff8000000000000LL);
+          }
+        } else {
+          ++n_steps[u];
+          t[u] = t_new;
+#pragma unroll
+          for (int n = 0; n < N; ++n) {
+            p[u][n] = y[u][n];
+            d[u][n] = d_new[n];
+          }
+        }
+      }
+    }
+  }
+
+  __device__ void run() {
+#pragma unroll
+    for (int u = 0; u < TPT; ++u) {
+      active[u] = false;
+      t[u] = 0.0;
+      h_auto[u] = 0.0;
+#pragma unroll
+      for (int n = 0; n < N; ++n) p[u][n] = d[u][n] = 0.0;
+#pragma unroll
+      for (int n = 0; n < NP; ++n) prm[u][n] = 0.0;
+      fetch(u);
+    }
+    while (true) {
+      bool any = false;
+#pragma unroll
+      for (int u = 0; u < TPT; ++u) {
+        while (active[u] && !(t[u] < A.t1)) {  // solver.rs:292
+          store(u);
+          fetch(u);
+        }
+        any = any || active[u];
+      }
+      if (!any) break;
+      attempt();
+    }
+  }
+};
+
+template <class Sys, int S, unsigned long long AMASK, unsigned BMASK, unsigned EMASK, int BLOCK, int TPT>
+__global__ void __launch_bounds__(BLOCK)
+    ode_adaptive_kernel(const __grid_constant__ OdeAdaptiveArgs A) {
+  OdeAdaptiveStepper<Sys, S, AMASK, BMASK, EMASK, TPT> st(A);
+  st.run();
+}
+
+}  // namespace DFB_NS

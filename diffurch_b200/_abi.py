@@ -147,7 +147,7 @@ class Totals(C.Structure):
         ("steps", C.c_uint64), ("rejected", C.c_uint64), ("events", C.c_uint64),
         ("rhs_evals", C.c_uint64), ("n_failed", C.c_uint64),
         ("kernel_ms", C.c_double),
-        ("kernel_launches", C.c_uint32), ("_pad", C.c_uint32),
+        ("kernel_launches", C.c_uint32), ("kernel_kind", C.c_uint32),
     ]
 
 

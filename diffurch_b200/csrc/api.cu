@@ -28,12 +28,24 @@ int run_ode_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t
                        size_t n, const double* y0, const double* params, double* t_final,
                        double* y_final, unsigned long long* steps, unsigned long long* rhs_evals,
                        uint32_t* status, cudaStream_t stream);
+int run_ode_fixed_periodic_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h,
+                                size_t n, const double* y0, const double* params, double* t_final,
+                                double* y_final, double* aux_final, unsigned long long* steps,
+                                unsigned long long* events, unsigned long long* rhs_evals,
+                                uint32_t* status, int n_loc, const dfb_locator* loc, int event_capacity,
+                                double* ev_t, int32_t* ev_idx, uint32_t* n_events, cudaStream_t stream);
 }
 namespace dfb_fast {
 int run_ode_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h,
                        size_t n, const double* y0, const double* params, double* t_final,
                        double* y_final, unsigned long long* steps, unsigned long long* rhs_evals,
                        uint32_t* status, cudaStream_t stream);
+int run_ode_fixed_periodic_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h,
+                                size_t n, const double* y0, const double* params, double* t_final,
+                                double* y_final, double* aux_final, unsigned long long* steps,
+                                unsigned long long* events, unsigned long long* rhs_evals,
+                                uint32_t* status, int n_loc, const dfb_locator* loc, int event_capacity,
+                                double* ev_t, int32_t* ev_idx, uint32_t* n_events, cudaStream_t stream);
 }
 
 namespace dfb_fast {
@@ -43,6 +55,11 @@ int run_dde_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t
                        double* y_final, unsigned long long* steps, unsigned long long* rhs_evals,
                        uint32_t* status, cudaStream_t stream);
 size_t dde_fixed_ring_doubles(int n_state, int I, int capacity);
+int run_ode_adaptive_shim(int system_id, const dfb_tableau& rk, const dfb_auto_stepsize& ctl, double t0,
+                          double t1, size_t n, const double* y0, const double* params, double* t_final,
+                          double* y_final, unsigned long long* steps, unsigned long long* rejected,
+                          unsigned long long* rhs_evals, uint32_t* status, unsigned long long* queue,
+                          int n_sm, cudaStream_t stream);
 }
 
 namespace {
@@ -164,12 +181,15 @@ struct dfb_handle {
   bool dde_hot = false;
   double* d_disco_t = nullptr;
   int32_t* d_disco_ord = nullptr;
+  unsigned long long* d_queue = nullptr;  // work counter of the dynamically scheduled kernels
+  int n_sm = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t stream = nullptr;
   unsigned launches = 0;
   int locate_batch = 32;     // lanes parked on a detected event before the warp runs its bisections
   int locate_max_wait = 16;  // ... or step rounds the first parked lane has waited (DFB_LOCATE_WAIT)
   bool used_hot_path = false;
+  uint32_t kernel_kind = DFB_KERNEL_GENERAL;
 };
 
 namespace {
@@ -185,7 +205,7 @@ void free_all(dfb_handle* h) {
                   h->d_aux,     h->d_steps,   h->d_rejected, h->d_events,  h->d_rhs,
                   h->d_status,  h->d_trace_t, h->d_trace_y,  h->d_nsamples, h->d_ev_t,
                   h->d_ev_idx,  h->d_nevents, h->d_ring_t,   h->d_ring_y,  h->d_ring_k,
-                  h->d_disco_t, h->d_disco_ord, h->d_ring_coeff};
+                  h->d_disco_t, h->d_disco_ord, h->d_ring_coeff, h->d_queue};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -375,6 +395,11 @@ int dfb_create(const dfb_problem* desc, size_t n_traj, int device, dfb_handle** 
   H_ALLOC(h->d_aux, n * size_t(info->n_aux));
   H_ALLOC(h->d_steps, n);
   H_ALLOC(h->d_rejected, n);
+  H_ALLOC(h->d_queue, 1);
+  {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->n_sm = prop.multiProcessorCount;
+  }
   H_ALLOC(h->d_events, n);
   H_ALLOC(h->d_rhs, n);
   H_ALLOC(h->d_status, n);
@@ -514,6 +539,7 @@ int dfb_run(dfb_handle* h, void* stream_v) {
                             !h->info.uses_history && p.trace_every == 0 && p.max_steps == 0 &&
                             p.history_id == DFB_HIST_CONSTANT && !std::getenv("DFB_FORCE_GENERAL");
   h->used_hot_path = false;
+  h->kernel_kind = DFB_KERNEL_GENERAL;
   if (hot_eligible) {
     DFB_CUDA(cudaMemsetAsync(h->d_rejected, 0, n * sizeof(unsigned long long), stream));
     DFB_CUDA(cudaMemsetAsync(h->d_events, 0, n * sizeof(unsigned long long), stream));
@@ -527,10 +553,62 @@ int dfb_run(dfb_handle* h, void* stream_v) {
       DFB_CUDA(cudaEventRecord(h->ev1, stream));
       h->launches = 1;
       h->used_hot_path = true;
+      h->kernel_kind = DFB_KERNEL_ODE_FIXED;
       h->ran = true;
       return DFB_OK;
     }
     // rc == -1: no specialised kernel -> general path below
+  }
+
+  // Fixed step + Periodic callbacks (dev/ode_fixed.cuh, OdeFixedPeriodicStepper): the Lyapunov-batch
+  // shape.  Every locator must be an unfiltered Periodic; final state / aux / event log only.
+  bool periodic_eligible = p.stepsize_kind == DFB_STEP_FIXED && p.n_loc > 0 && !h->info.uses_history &&
+                           p.trace_every == 0 && p.max_steps == 0 && p.history_id == DFB_HIST_CONSTANT &&
+                           !std::getenv("DFB_FORCE_GENERAL");
+  for (int l = 0; l < p.n_loc && periodic_eligible; ++l)
+    periodic_eligible = p.loc[l].kind == DFB_LOC_PERIODIC && p.loc[l].filter == DFB_FILTER_NONE;
+  if (periodic_eligible) {
+    DFB_CUDA(cudaMemsetAsync(h->d_rejected, 0, n * sizeof(unsigned long long), stream));
+    DFB_CUDA(cudaEventRecord(h->ev0, stream));
+    auto shim = p.arith == DFB_ARITH_FAST ? dfb_fast::run_ode_fixed_periodic_shim
+                                          : dfb_strict::run_ode_fixed_periodic_shim;
+    const int rc = shim(p.system_id, p.rk, p.t0, p.t1, p.h, n, y0, params, h->d_t, h->d_y,
+                        h->info.n_aux ? h->d_aux : nullptr, h->d_steps, h->d_events, h->d_rhs, h->d_status,
+                        p.n_loc, p.loc, p.event_capacity, h->d_ev_t, h->d_ev_idx, h->d_nevents, stream);
+    if (rc > 0) return fail(DFB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(cudaError_t(rc)));
+    if (rc == 0) {
+      DFB_CUDA(cudaEventRecord(h->ev1, stream));
+      h->launches = 1;
+      h->used_hot_path = true;
+      h->kernel_kind = DFB_KERNEL_ODE_FIXED_PERIODIC;
+      h->ran = true;
+      return DFB_OK;
+    }
+  }
+
+  // Adaptive hot path (dev/ode_adaptive.cuh): AutomaticStepsize, no locators, no history,
+  // final state only, FAST arithmetic.
+  const bool adaptive_eligible = p.stepsize_kind == DFB_STEP_AUTOMATIC && p.n_loc == 0 &&
+                                 !h->info.uses_history && p.trace_every == 0 && p.max_steps == 0 &&
+                                 p.history_id == DFB_HIST_CONSTANT && p.arith == DFB_ARITH_FAST &&
+                                 !std::getenv("DFB_FORCE_GENERAL");
+  if (adaptive_eligible) {
+    DFB_CUDA(cudaMemsetAsync(h->d_events, 0, n * sizeof(unsigned long long), stream));
+    if (h->info.n_aux) DFB_CUDA(cudaMemsetAsync(h->d_aux, 0, n * h->info.n_aux * sizeof(double), stream));
+    DFB_CUDA(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned long long), stream));
+    DFB_CUDA(cudaEventRecord(h->ev0, stream));
+    const int rc = dfb_fast::run_ode_adaptive_shim(p.system_id, p.rk, p.automatic, p.t0, p.t1, n, y0, params,
+                                                   h->d_t, h->d_y, h->d_steps, h->d_rejected, h->d_rhs,
+                                                   h->d_status, h->d_queue, h->n_sm, stream);
+    if (rc > 0) return fail(DFB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(cudaError_t(rc)));
+    if (rc == 0) {
+      DFB_CUDA(cudaEventRecord(h->ev1, stream));
+      h->launches = 1;
+      h->used_hot_path = true;
+      h->kernel_kind = DFB_KERNEL_ODE_ADAPTIVE;
+      h->ran = true;
+      return DFB_OK;
+    }
   }
 
   if (h->dde_hot) {
@@ -546,6 +624,7 @@ int dfb_run(dfb_handle* h, void* stream_v) {
     DFB_CUDA(cudaEventRecord(h->ev1, stream));
     h->launches = 1;
     h->used_hot_path = true;
+    h->kernel_kind = DFB_KERNEL_DDE_FIXED;
     h->ran = true;
     return DFB_OK;
   }
@@ -677,6 +756,7 @@ int dfb_get_totals(dfb_handle* h, dfb_totals* out) {
   DFB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   out->kernel_ms = ms;
   out->kernel_launches = h->launches;
+  out->kernel_kind = h->kernel_kind;
   return DFB_OK;
 }
 

@@ -354,8 +354,9 @@ struct Integrator {
     return P.stepsize_kind == DFB_STEP_AUTOMATIC ? h_auto : P.h;
   }
   // AutomaticStepsize::update (stepsize.rs:64-85); true = Rejected
-  __device__ bool stepsize_update_rejects() {
+  __device__ bool stepsize_update_rejects(double* h_before) {
     const dfb_auto_stepsize& A = P.automatic;
+    *h_before = h_auto;
     double err = 0.0;
 #pragma unroll
     for (int n = 0; n < N; ++n) {
@@ -698,6 +699,7 @@ struct Integrator {
       // (2) one make_step for every lane that can advance
       if (mode == MODE_STEP || mode == MODE_EVENT_RESTEP) {
         const bool restep = mode == MODE_EVENT_RESTEP;
+        double h_before = 0.0;
         const double h_req = restep ? (ev_time - t_curr) : fmin(stepsize_get(), P.t1 - t_curr);
         make_step(h_req, adaptive);
         if (hist.status & (DFB_TRAJ_HISTORY_DELETED | DFB_TRAJ_HISTORY_NOT_READY |
@@ -720,9 +722,17 @@ struct Integrator {
           ++n_steps;
           on_step();
           mode = next_mode();
-        } else if (adaptive && stepsize_update_rejects()) {
+        } else if (adaptive && stepsize_update_rejects(&h_before)) {
           ++n_rejected;
           undo_step();  // solver.rs:294-297
+          // a rejection that leaves the controller's stepsize unchanged (clamped at
+          // stepsize_range.start) repeats the same step from the same state: the reference would
+          // retry forever; stop the trajectory instead (DFB_TRAJ_STEPSIZE_FLOOR)
+          if (h_auto == h_before) {
+            hist.status |= DFB_TRAJ_STEPSIZE_FLOOR;
+            t_curr = dev_nan();
+            mode = MODE_DONE;
+          }
         } else {
           fired_mask = 0u;
           if (HAS_LOC) {

@@ -39,6 +39,15 @@ struct OdeFixedArgs {
   unsigned long long* steps;
   unsigned long long* rhs_evals;
   uint32_t* status;
+  // ---- time-only events (ode_fixed_periodic_kernel): Periodic locators + their callbacks
+  int32_t n_loc;
+  int32_t event_capacity;
+  dfb_locator loc[DFB_MAX_LOCATORS];
+  double* aux_final;             // [A][n]
+  unsigned long long* events;    // [n]
+  double* ev_t;                  // [ecap][n]
+  int32_t* ev_idx;               // [ecap][n]
+  uint32_t* n_events;            // [n]
 };
 
 __host__ __device__ constexpr unsigned long long amask_bit(int i, int j) { return 1ull << (i * 8 + j); }
@@ -202,6 +211,200 @@ __global__ void __launch_bounds__(BLOCK)
   }
   if (!valid[0]) return;
   OdeFixedStepper<Sys, S, AMASK, BMASK, PRESCALED, TPT> st(A);
+  st.run(gid, valid);
+}
+
+// ---------------------------------------------------------------------------------------
+// Fixed step + time-only events: every locator is a `Periodic` (loc.rs:292-335), the shape of
+// every Lyapunov-exponent run in the reference (tests/lyapunov_exponents.rs: integrate the
+// variational system, re-orthonormalise with a QR every `period`).  Detection and location of
+// a Periodic depend on the time grid only, and with a fixed step the time grid is the same for
+// every member of the ensemble, so the whole event machinery of Solver::run (solver.rs:299-307:
+// locate earliest -> undo -> step to the event time -> commit -> zero step -> callback ->
+// commit) is WARP-UNIFORM control flow around the register-resident stepper above: no lane
+// parks, no divergence, and the state never leaves registers.  Only the callback's
+// `stop_integration` is per lane (a stopped lane stores its result and idles).
+template <class Sys, int S, unsigned long long AMASK, unsigned BMASK, bool PRESCALED, int TPT>
+struct OdeFixedPeriodicStepper : OdeFixedStepper<Sys, S, AMASK, BMASK, PRESCALED, TPT> {
+  using Base = OdeFixedStepper<Sys, S, AMASK, BMASK, PRESCALED, TPT>;
+  static constexpr int N = Sys::N;
+  static constexpr int NA = Sys::NA > 0 ? Sys::NA : 1;
+  using RefMut = StateRefMut<N, NoHist>;
+  using Base::A;
+  using Base::d_curr;
+  using Base::k;
+  using Base::p_curr;
+  using Base::p_prev;
+  using Base::prm;
+  using Base::t_curr;
+  using Base::t_prev;
+
+  double aux[TPT][NA];
+  bool alive[TPT];
+
+  __device__ explicit OdeFixedPeriodicStepper(const OdeFixedArgs& A_) : Base(A_) {}
+
+  __device__ void store(int u, size_t gid, double t_fin, unsigned long long n_steps,
+                        unsigned long long n_events, unsigned long long n_rhs, uint32_t n_evlog) {
+    const size_t n_traj = A.n_traj;
+    bool finite = true;
+#pragma unroll
+    for (int n = 0; n < N; ++n)
+      finite = finite && (fabs(p_curr[u][n]) < __longlong_as_double(0x7ff0000000000000LL));
+    uint32_t status = finite ? 0u : uint32_t(DFB_TRAJ_NONFINITE);
+    if (t_fin == __longlong_as_double(0x7ff0000000000000LL)) status |= DFB_TRAJ_STOPPED;
+    A.t_final[gid] = t_fin;
+#pragma unroll
+    for (int n = 0; n < N; ++n) A.y_final[size_t(n) * n_traj + gid] = p_curr[u][n];
+    if (A.aux_final) {
+#pragma unroll
+      for (int n = 0; n < Sys::NA; ++n) A.aux_final[size_t(n) * n_traj + gid] = aux[u][n];
+    }
+    A.steps[gid] = n_steps;
+    A.events[gid] = n_events;
+    A.rhs_evals[gid] = n_rhs;
+    A.status[gid] = status;
+    if (A.n_events) A.n_events[gid] = n_evlog;
+  }
+
+  __device__ void run(const size_t* gid, const bool* valid) {
+    const size_t n_traj = A.n_traj;
+#pragma unroll
+    for (int u = 0; u < TPT; ++u) {
+#pragma unroll
+      for (int n = 0; n < Sys::NP; ++n) prm[u][n] = A.params[size_t(n) * n_traj + gid[u]];
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        p_curr[u][n] = p_prev[u][n] = A.y0[size_t(n) * n_traj + gid[u]];
+        d_curr[u][n] = 0.0;
+      }
+#pragma unroll
+      for (int n = 0; n < NA; ++n) aux[u][n] = 0.0;
+      alive[u] = valid[u];
+    }
+    t_curr = t_prev = A.t0;
+    // uniform bookkeeping (identical in every lane)
+    unsigned long long n_steps = 0, n_events = 0, n_rhs = 0;
+    uint32_t n_evlog = 0u;
+    double last_call[DFB_MAX_LOCATORS];
+    uint32_t has_last_call = 0u;
+#pragma unroll
+    for (int l = 0; l < DFB_MAX_LOCATORS; ++l) last_call[l] = 0.0;
+    const double h = A.h;
+
+#pragma unroll 1
+    while (t_curr < A.t1) {
+      bool any_alive = false;
+#pragma unroll
+      for (int u = 0; u < TPT; ++u) any_alive = any_alive || alive[u];
+      if (!__any_sync(0xffffffffu, any_alive)) break;  // every member of the warp stopped itself
+
+      if (t_prev == t_curr) {  // state.rs:97-98: k[0] evaluated by make_step itself
+        this->rhs_all(d_curr);
+        ++n_rhs;
+      }
+      const double h_req = fmin(h, A.t1 - t_curr);  // solver.rs:293
+      if (h_req == h) this->template step<true>(h);
+      else this->template step<false>(h_req);
+      n_rhs += S;
+
+      // HListLocateEarliest over Periodic locators (loc.rs:318-334, 821-835, 1002-1011)
+      bool found = false;
+      double best_t = 0.0;
+      int best_l = 0;
+#pragma unroll
+      for (int l = 0; l < DFB_MAX_LOCATORS; ++l) {
+        if (l >= A.n_loc) break;
+        const dfb_locator& L = A.loc[l];
+        if (L.dedup && ((has_last_call >> l) & 1u) && !(t_prev > last_call[l])) continue;
+        const double fl_prev = floor((t_prev - L.offset) / L.period);
+        const double fl_curr = floor((t_curr - L.offset) / L.period);
+        if (fl_prev < fl_curr) {
+          const double tl = fl_curr * L.period + L.offset;
+          if (!found || tl < best_t) {
+            found = true;
+            best_t = tl;
+            best_l = l;
+          }
+        }
+      }
+      if (found && best_t >= t_prev) {  // solver.rs:299-307
+        // undo_step (state.rs:146-150); k[0] still holds d_prev
+        t_curr = t_prev;
+#pragma unroll
+        for (int u = 0; u < TPT; ++u)
+#pragma unroll
+          for (int n = 0; n < N; ++n) {
+            p_curr[u][n] = p_prev[u][n];
+            d_curr[u][n] = k[u][0][n];
+          }
+        this->rhs_all(d_curr);  // t_prev == t_curr: make_step evaluates k[0] again
+        ++n_rhs;
+        this->template step<false>(best_t - t_curr);
+        n_rhs += S;
+        // commit_step; make_zero_step (state.rs:141-144)
+        t_prev = t_curr;
+#pragma unroll
+        for (int u = 0; u < TPT; ++u)
+#pragma unroll
+          for (int n = 0; n < N; ++n) p_prev[u][n] = p_curr[u][n];
+        // callback of the located event (LocCallback / DedupLocF::eval_mut, loc.rs:1023-1026)
+        const dfb_locator& L = A.loc[best_l];
+        if (L.dedup) {
+          has_last_call |= 1u << best_l;
+          last_call[best_l] = t_curr;
+        }
+        ++n_events;
+        if (A.event_capacity > 0) {
+          if (n_evlog < uint32_t(A.event_capacity)) {
+#pragma unroll
+            for (int u = 0; u < TPT; ++u)
+              if (alive[u]) {
+                A.ev_t[size_t(n_evlog) * n_traj + gid[u]] = best_t;
+                A.ev_idx[size_t(n_evlog) * n_traj + gid[u]] = best_l;
+              }
+          }
+          ++n_evlog;
+        }
+        ++n_steps;  // the second commit_step of the event (solver.rs:308)
+        if (L.callback_id != DFB_CB_NONE) {
+#pragma unroll
+          for (int u = 0; u < TPT; ++u) {
+            double t_lane = t_curr;
+            RefMut m{&t_lane, p_curr[u], d_curr[u], t_prev, p_prev[u], &this->nohist};
+            Sys::callback(L.callback_id, m, prm[u], aux[u]);
+            if (t_lane != t_curr && alive[u]) {  // stop_integration (state_fn.rs:92-97) or a moved clock
+              store(u, gid[u], t_lane, n_steps, n_events, n_rhs, n_evlog);
+              alive[u] = false;
+            }
+          }
+        }
+      } else {
+        ++n_steps;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < TPT; ++u)
+      if (alive[u]) store(u, gid[u], t_curr, n_steps, n_events, n_rhs, n_evlog);
+  }
+};
+
+template <class Sys, int S, unsigned long long AMASK, unsigned BMASK, bool PRESCALED, int BLOCK, int TPT>
+__global__ void __launch_bounds__(BLOCK)
+    ode_fixed_periodic_kernel(const __grid_constant__ OdeFixedArgs A) {
+  const size_t g = size_t(blockIdx.x) * BLOCK + threadIdx.x;
+  const size_t stride = size_t(gridDim.x) * BLOCK;
+  size_t gid[TPT];
+  bool valid[TPT];
+#pragma unroll
+  for (int u = 0; u < TPT; ++u) {
+    const size_t i = g + size_t(u) * stride;
+    valid[u] = i < A.n_traj;
+    gid[u] = valid[u] ? i : A.n_traj - 1;
+  }
+  // whole warps stay (the loop votes); lanes past the end replay the last member and store nothing
+  if ((g & ~size_t(31)) >= A.n_traj) return;
+  OdeFixedPeriodicStepper<Sys, S, AMASK, BMASK, PRESCALED, TPT> st(A);
   st.run(gid, valid);
 }
 

@@ -132,6 +132,8 @@ __device__ inline void dev_householder_qr3(double* m, double* rdiag) {
 struct SysBase {
   static constexpr int NP = 0, NA = 0, ND = 0, NC = 0;
   static constexpr bool uses_history = false;
+  // rhs depends on (t, p, params) only: not on the stale d, p_prev/t_prev or the history
+  static constexpr bool pure_rhs = true;
   template <class V>
   __device__ static double detector(int, const V&, const double*) { return 0.0; }
   template <class M>
@@ -276,6 +278,7 @@ struct SysZero1 : SysBase {  // tests/delay_propagation.rs:13, :86
 struct SysDdeLinear : SysBase {  // tests/equation_types.rs:131
   static constexpr int ID = DFB_SYS_DDE_LINEAR, N = 1, NP = 4;
   static constexpr bool uses_history = true;
+  static constexpr bool pure_rhs = false;
   // the one constant delay of this equation (lets the streaming-window kernel take it)
   __device__ __forceinline__ static double const_delay(const double* prm) { return prm[2]; }
   template <class V>
@@ -289,6 +292,7 @@ struct SysDdeLinear : SysBase {  // tests/equation_types.rs:131
 struct SysNddeLinear : SysBase {  // tests/equation_types.rs:150
   static constexpr int ID = DFB_SYS_NDDE_LINEAR, N = 1, NP = 4;
   static constexpr bool uses_history = true;
+  static constexpr bool pure_rhs = false;
   __device__ __forceinline__ static double const_delay(const double* prm) { return prm[2]; }
   template <class V>
   __device__ __forceinline__ static void rhs(const V& s, const double* prm, double* out) {
@@ -353,6 +357,7 @@ struct SysEggBilliard : SysBase {  // examples/egg-billiard.rs:12-40
 
 struct SysRelayMsign : SysBase {  // examples/ode-2-relay-msign.rs:17-20
   static constexpr int ID = DFB_SYS_RELAY_MSIGN, N = 2, ND = 1;
+  static constexpr bool pure_rhs = false;  // reads p_prev
   template <class V>
   __device__ __forceinline__ static void rhs(const V& s, const double*, double* out) {
     out[0] = s.p[1];
@@ -365,6 +370,7 @@ struct SysRelayMsign : SysBase {  // examples/ode-2-relay-msign.rs:17-20
 struct SysDdeRelayClamp : SysBase {  // examples/dde-relay-clamp.rs:24-35
   static constexpr int ID = DFB_SYS_DDE_RELAY_CLAMP, N = 2, NP = 3, ND = 1;
   static constexpr bool uses_history = true;
+  static constexpr bool pure_rhs = false;
   template <class V>
   __device__ __forceinline__ static void rhs(const V& s, const double* prm, double* out) {
     const double x = s.p[0], dx = s.p[1];

@@ -4,6 +4,7 @@
 #include "launch.hpp"
 
 #include <cstdlib>
+#include <cstring>
 
 namespace DFB_NS {
 
@@ -57,6 +58,49 @@ bool launch_all_shapes(int S, unsigned long long am, unsigned bm, const OdeFixed
 }
 }  // namespace
 
+// ---- fixed step + Periodic callbacks (ode_fixed_periodic_kernel) -----------------------
+namespace {
+template <class Sys, int S, unsigned long long AMASK, unsigned BMASK>
+bool try_launch_periodic(int S_rt, unsigned long long amask, unsigned bmask, const OdeFixedArgs& A,
+                         cudaStream_t stream, int* rc) {
+  if (S_rt != S) return false;
+  if ((amask & ~AMASK) != 0ull || (bmask & ~BMASK) != 0u) return false;
+  const size_t grid = (A.n_traj + kBlock - 1) / kBlock;
+  ode_fixed_periodic_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 1><<<unsigned(grid), kBlock, 0, stream>>>(A);
+  *rc = int(cudaGetLastError());
+  return true;
+}
+template <class Sys>
+bool launch_periodic_common(int S, unsigned long long am, unsigned bm, const OdeFixedArgs& A,
+                            cudaStream_t st, int* rc) {
+  return try_launch_periodic<Sys, 7, amask_full_lower(7), 0x7Du>(S, am, bm, A, st, rc) ||  // rktp64
+         try_launch_periodic<Sys, 4, amask_full_lower(4), 0xFu>(S, am, bm, A, st, rc);      // rk4 family
+}
+}  // namespace
+
+int launch_ode_fixed_periodic(int system_id, int S, unsigned long long amask, unsigned bmask,
+                              const OdeFixedArgs& A, cudaStream_t stream) {
+  int rc = 0;
+  bool ok = false;
+  switch (system_id) {
+    case DFB_SYS_LORENZ_VARIATIONAL:
+      ok = launch_periodic_common<SysLorenzVariational>(S, amask, bmask, A, stream, &rc);
+      break;
+    case DFB_SYS_LINEAR1: ok = launch_periodic_common<SysLinear1>(S, amask, bmask, A, stream, &rc); break;
+    case DFB_SYS_LINEAR1_SIN: ok = launch_periodic_common<SysLinear1Sin>(S, amask, bmask, A, stream, &rc); break;
+    case DFB_SYS_LINEAR3: ok = launch_periodic_common<SysLinear3>(S, amask, bmask, A, stream, &rc); break;
+    case DFB_SYS_LINEAR3_MATRIX:
+      ok = launch_periodic_common<SysLinear3Matrix>(S, amask, bmask, A, stream, &rc);
+      break;
+    case DFB_SYS_LORENZ: ok = launch_periodic_common<SysLorenz>(S, amask, bmask, A, stream, &rc); break;
+    case DFB_SYS_EGG_BILLIARD:  // its callback calls stop_integration: exercises the per-lane stop
+      ok = try_launch_periodic<SysEggBilliard, 7, amask_full_lower(7), 0x7Du>(S, amask, bmask, A, stream, &rc);
+      break;
+    default: break;
+  }
+  return ok ? rc : -1;
+}
+
 // returns 0 = launched, >0 = CUDA error code, -1 = no compiled kernel for this combination
 int launch_ode_fixed(int system_id, int S, unsigned long long amask, unsigned bmask,
                      const OdeFixedArgs& A, cudaStream_t stream) {
@@ -81,11 +125,12 @@ int launch_ode_fixed(int system_id, int S, unsigned long long amask, unsigned bm
 
 // Host shim used by api.cu: builds the argument block (pre-scaled rows are
 // computed here with plain IEEE double multiplies) and launches.
-int run_ode_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h,
-                       size_t n, const double* y0, const double* params, double* t_final,
-                       double* y_final, unsigned long long* steps, unsigned long long* rhs_evals,
-                       uint32_t* status, cudaStream_t stream) {
-  OdeFixedArgs A;
+namespace {
+void fill_args(OdeFixedArgs& A, unsigned long long* amask_out, unsigned* bmask_out, const dfb_tableau& rk,
+               double t0, double t1, double h, size_t n, const double* y0, const double* params,
+               double* t_final, double* y_final, unsigned long long* steps,
+               unsigned long long* rhs_evals, uint32_t* status) {
+  std::memset(&A, 0, sizeof(A));
   unsigned long long amask = 0;
   unsigned bmask = 0;
   for (int i = 0; i < DFB_MAX_STAGES; ++i) {
@@ -112,7 +157,42 @@ int run_ode_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t
   A.steps = steps;
   A.rhs_evals = rhs_evals;
   A.status = status;
+  *amask_out = amask;
+  *bmask_out = bmask;
+}
+}  // namespace
+
+int run_ode_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h,
+                       size_t n, const double* y0, const double* params, double* t_final,
+                       double* y_final, unsigned long long* steps, unsigned long long* rhs_evals,
+                       uint32_t* status, cudaStream_t stream) {
+  OdeFixedArgs A;
+  unsigned long long amask = 0;
+  unsigned bmask = 0;
+  fill_args(A, &amask, &bmask, rk, t0, t1, h, n, y0, params, t_final, y_final, steps, rhs_evals, status);
   return launch_ode_fixed(system_id, rk.S, amask, bmask, A, stream);
+}
+
+// Fixed step + Periodic locators (all `n_loc` entries of `loc` are DFB_LOC_PERIODIC, unfiltered).
+int run_ode_fixed_periodic_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h,
+                                size_t n, const double* y0, const double* params, double* t_final,
+                                double* y_final, double* aux_final, unsigned long long* steps,
+                                unsigned long long* events, unsigned long long* rhs_evals,
+                                uint32_t* status, int n_loc, const dfb_locator* loc, int event_capacity,
+                                double* ev_t, int32_t* ev_idx, uint32_t* n_events, cudaStream_t stream) {
+  OdeFixedArgs A;
+  unsigned long long amask = 0;
+  unsigned bmask = 0;
+  fill_args(A, &amask, &bmask, rk, t0, t1, h, n, y0, params, t_final, y_final, steps, rhs_evals, status);
+  A.n_loc = n_loc;
+  for (int l = 0; l < n_loc && l < DFB_MAX_LOCATORS; ++l) A.loc[l] = loc[l];
+  A.event_capacity = ev_t ? event_capacity : 0;
+  A.aux_final = aux_final;
+  A.events = events;
+  A.ev_t = ev_t;
+  A.ev_idx = ev_idx;
+  A.n_events = n_events;
+  return launch_ode_fixed_periodic(system_id, rk.S, amask, bmask, A, stream);
 }
 
 }  // namespace DFB_NS

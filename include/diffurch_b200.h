@@ -69,6 +69,10 @@ typedef enum dfb_status {
 #define DFB_TRAJ_RING_OVERFLOW 32u     /* history ring capacity exceeded (library limit) */
 #define DFB_TRAJ_STOPPED 64u           /* StateRefMut::stop_integration (state_fn.rs:92-97) */
 #define DFB_TRAJ_DISCO_OVERFLOW 128u   /* discontinuity list capacity exceeded */
+#define DFB_TRAJ_STEPSIZE_FLOOR 256u   /* AutomaticStepsize rejected a step and could not shrink its
+                                          stepsize (clamped at stepsize_range.start): the reference's
+                                          retry loop (solver.rs:294-297) never ends here; the trajectory
+                                          is stopped with t = NaN */
 
 /* ---------------------------------------------------------------- tableau */
 /* Mirror of `ButcherTableu<T,S,I>` (rk.rs:5-14).  Row-major, padded to the
@@ -297,8 +301,18 @@ typedef struct dfb_totals {
   uint64_t n_failed;       /* trajectories with any status bit except STOPPED */
   double kernel_ms;        /* CUDA-event duration of the integration kernel(s) */
   uint32_t kernel_launches;
-  uint32_t _pad;
+  uint32_t kernel_kind;    /* dfb_kernel_kind: which kernel family integrated the ensemble */
 } dfb_totals;
+
+/* Kernel families (all CUDA; there is no CPU path). */
+typedef enum dfb_kernel_kind {
+  DFB_KERNEL_GENERAL = 0,      /* integrate_general_kernel: every Solver feature */
+  DFB_KERNEL_ODE_FIXED = 1,    /* ode_fixed_kernel: fixed step, registers only */
+  DFB_KERNEL_DDE_FIXED = 2,    /* dde_fixed_kernel: constant delay, coefficient ring */
+  DFB_KERNEL_ODE_ADAPTIVE = 3, /* ode_adaptive_kernel: AutomaticStepsize, dynamic trajectory queue */
+  DFB_KERNEL_ODE_FIXED_PERIODIC = 4 /* ode_fixed_periodic_kernel: fixed step + Periodic callbacks
+                                       (warp-uniform event handling; the Lyapunov-batch shape) */
+} dfb_kernel_kind;
 
 /* Solver::new + setters -> one handle for `n_traj` trajectories on `device`. */
 DFB_API int dfb_create(const dfb_problem* desc, size_t n_traj, int device, dfb_handle** out);

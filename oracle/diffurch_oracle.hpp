@@ -144,6 +144,7 @@ enum TrajStatus : uint32_t {
   TRAJ_NONFINITE = 8,
   TRAJ_STEP_LIMIT = 16,
   TRAJ_STOPPED = 64,
+  TRAJ_STEPSIZE_FLOOR = 256,
 };
 struct Panic {
   uint32_t status;
@@ -837,9 +838,16 @@ struct Solver {
     fire(events_on_step, state);
     while (state.t_curr < t_end) {
       state.make_step(rhs, std::fmin(stepsize.get(), t_end - state.t_curr));
+      double h_ctl = stepsize.get();
       while (stepsize.update(state.e_curr) == StepStatus::Rejected) {
         ++n_rejected;
         state.undo_step();
+        // Not a reference behaviour: when a rejection leaves the controller's stepsize unchanged
+        // (clamped at stepsize_range.start) the retry is the same step from the same state with the
+        // same error, and the reference's loop never ends.  The CUDA path stops such a trajectory
+        // with DFB_TRAJ_STEPSIZE_FLOOR; so does this checker.
+        if (stepsize.get() == h_ctl) throw Panic{TRAJ_STEPSIZE_FLOOR};
+        h_ctl = stepsize.get();
         state.make_step(rhs, std::fmin(stepsize.get(), t_end - state.t_curr));
       }
       size_t index;

@@ -445,6 +445,146 @@ def test_adaptive_lorenz_short(oracle):
     assert np.max(np.abs(g.p - o.p) / np.maximum(np.abs(o.p), 1.0)) < 1e-7
 
 
+
+# ---------------------------------------------------------------- adaptive hot path (ode_adaptive_kernel)
+KERNEL_GENERAL, KERNEL_ODE_FIXED, KERNEL_DDE_FIXED, KERNEL_ODE_ADAPTIVE = 0, 1, 2, 3
+
+
+def check_adaptive_counters(g, S):
+    # rhs evaluations as the reference counts them: S per attempt, k[0] at the start and after every undo
+    att = g.steps + g.rejected
+    assert np.array_equal(g.rhs_evals, att * S + 1 + g.rejected)
+
+
+def test_adaptive_hot_path_harmonic_vs_oracle(oracle):
+    # 257 members (ragged block) with different initial amplitudes -> different step sequences
+    amp = 1.0 + np.arange(257) / 64.0
+    y0 = np.stack([np.zeros(257), amp], axis=1)
+
+    def mk(arith="fast"):
+        return (d.Solver.new().initial(y0).equation(d.systems.Harmonic).interval(0.0, 10.0)
+                .stepsize(auto_stepsize(2)).arith(arith))
+    f = mk().run()
+    assert f.totals["kernel_kind"] == KERNEL_ODE_ADAPTIVE
+    o = oracle.run_solver(mk("strict"), n_threads=8)
+    assert np.all(f.status == 0)
+    check_adaptive_counters(f, 7)
+    # "adaptive ... within the solver tolerance" (atol = rtol = 1e-9): the controller's root is a
+    # Newton iteration instead of libm pow, so a step count may differ by one near err = 1
+    assert np.max(np.abs(f.steps.astype(np.int64) - o.steps.astype(np.int64))) <= 1
+    assert np.max(np.abs(f.rejected.astype(np.int64) - o.rejected.astype(np.int64))) <= 1
+    assert np.array_equal(f.t, o.t)
+    assert np.max(np.abs(f.p - o.p)) < 1e-9
+    assert np.max(np.abs(f.p[:, 0] - amp * math.sin(10.0))) < 1e-6
+    # and against the general kernel in the same arithmetic
+    os.environ["DFB_FORCE_GENERAL"] = "1"
+    try:
+        gen = mk().run()
+    finally:
+        del os.environ["DFB_FORCE_GENERAL"]
+    assert gen.totals["kernel_kind"] == KERNEL_GENERAL
+    assert np.max(np.abs(f.p - gen.p)) < 1e-11
+    assert np.max(np.abs(f.steps.astype(np.int64) - gen.steps.astype(np.int64))) <= 1
+
+
+@pytest.mark.parametrize("rk,order", [("rktp64", 4), ("rk43", 3), ("rk4", 2), ("heun2", 1), ("three_eights", 2)])
+def test_adaptive_hot_path_tableaux(oracle, rk, order):
+    lam = -0.5 - np.arange(100) / 50.0
+    ctl = d.AutomaticStepsize(stepsize=1e-2, stepsize_range=(1e-7, 1e-1), atol=[1e-8], rtol=[1e-8],
+                              order=order, fac=0.9, fac_range=(0.2, 5.0))
+
+    def mk(arith="fast"):
+        return (d.Solver.new().initial(np.ones((100, 1))).equation(d.systems.Linear1, lam.reshape(-1, 1))
+                .interval(0.0, 3.0).stepsize(ctl).rk(d.RK.by_name(rk)).arith(arith))
+    f = mk().run()
+    assert f.totals["kernel_kind"] == KERNEL_ODE_ADAPTIVE
+    o = oracle.run_solver(mk("strict"), n_threads=8)
+    assert np.all(f.status == 0) and np.all(o.status == 0)
+    check_adaptive_counters(f, d.RK.by_name(rk).S)
+    assert np.max(np.abs(f.steps.astype(np.int64) - o.steps.astype(np.int64))) <= 1
+    assert np.array_equal(f.t, o.t)
+    assert np.max(np.abs(f.p - o.p) / np.abs(o.p)) < 1e-8
+
+
+def test_adaptive_hot_path_lorenz_short(oracle):
+    def mk(arith="fast"):
+        return cases.lorenz(n=1000, t1=2.0, arith=arith).stepsize(auto_stepsize(3))
+    f = mk().run()
+    assert f.totals["kernel_kind"] == KERNEL_ODE_ADAPTIVE
+    o = oracle.run_solver(mk("strict"), n_threads=8)
+    assert np.all(f.status == 0)
+    check_adaptive_counters(f, 7)
+    assert np.max(np.abs(f.steps.astype(np.int64) - o.steps.astype(np.int64))) <= 1
+    assert np.max(np.abs(f.p - o.p) / np.maximum(np.abs(o.p), 1.0)) < 1e-7
+
+
+def test_adaptive_stepsize_floor_becomes_status_bit(oracle):
+    # a tolerance the smallest allowed step cannot meet: the reference retries forever
+    # (solver.rs:294-297); the library stops the trajectory with DFB_TRAJ_STEPSIZE_FLOOR
+    ctl = d.AutomaticStepsize(stepsize=1e-1, stepsize_range=(5e-2, 1e-1), atol=[1e-14] * 3, rtol=[1e-14] * 3,
+                              order=4, fac=0.9, fac_range=(0.2, 5.0))
+
+    def mk(arith):
+        return cases.lorenz(n=40, t1=2.0, arith=arith).stepsize(ctl)
+    o = oracle.run_solver(mk("strict"), n_threads=4)
+    g = mk("strict").run()   # general kernel
+    f = mk("fast").run()     # adaptive hot path
+    assert f.totals["kernel_kind"] == KERNEL_ODE_ADAPTIVE and g.totals["kernel_kind"] == KERNEL_GENERAL
+    for r in (o, g, f):
+        assert np.all(r.status & 256)
+    assert np.array_equal(g.steps, o.steps) and np.array_equal(g.rejected, o.rejected)
+    assert np.array_equal(f.steps, o.steps) and np.array_equal(f.rejected, o.rejected)
+    assert np.all(np.isnan(f.t)) and np.all(np.isnan(g.t))
+    # kutta3's "embedded" weights b2 = [0, 1, 0] (rk.rs) give an O(h) error estimate: with tol = 1e-8
+    # the controller hits stepsize_range.start = 1e-7 at once (9 rejections, no accepted step)
+    lam = -0.5 - np.arange(50) / 50.0
+    ctl3 = d.AutomaticStepsize(stepsize=1e-2, stepsize_range=(1e-7, 1e-1), atol=[1e-8], rtol=[1e-8],
+                               order=1, fac=0.9, fac_range=(0.2, 5.0))
+
+    def mk3(arith):
+        return (d.Solver.new().initial(np.ones((50, 1))).equation(d.systems.Linear1, lam.reshape(-1, 1))
+                .interval(0.0, 3.0).stepsize(ctl3).rk(d.RK.kutta3()).arith(arith))
+    o3 = oracle.run_solver(mk3("strict"), n_threads=4)
+    f3 = mk3("fast").run()
+    assert f3.totals["kernel_kind"] == KERNEL_ODE_ADAPTIVE
+    assert np.all(o3.status == 256) and np.all(f3.status == 256)
+    assert np.array_equal(f3.steps, o3.steps) and np.array_equal(f3.rejected, o3.rejected)
+    assert np.all(f3.rejected == 9) and np.all(f3.steps == 0)
+
+
+def test_adaptive_hot_path_empty_interval_and_degenerate_errors():
+    # t1 == t0: no step, no rhs evaluation (solver.rs:292)
+    s = cases.lorenz(n=33, t1=0.0, arith="fast").stepsize(auto_stepsize(3)).run()
+    assert s.totals["kernel_kind"] == KERNEL_ODE_ADAPTIVE
+    assert np.all(s.steps == 0) and np.all(s.rhs_evals == 0) and np.all(s.t == 0.0)
+    assert np.array_equal(s.p, np.tile([1.0, 2.0, 20.0], (33, 1)))
+    # y' = 0 * y: the error estimate is exactly 0 -> err = 0/atol = 0 -> factor clamps to fac_max
+    z = (d.Solver.new().initial(np.ones((5, 1))).equation(d.systems.Linear1, np.zeros((5, 1)))
+         .interval(0.0, 1.0).stepsize(auto_stepsize(1)).arith("fast").run())
+    assert z.totals["kernel_kind"] == KERNEL_ODE_ADAPTIVE
+    assert np.all(z.status == 0) and np.all(z.p == 1.0) and np.all(z.t == 1.0)
+    # h: 1e-2 -> 5e-2 -> 1e-1 (stepsize_range end) ... : 1e-2, 5e-2, then 0.1 steps to t = 1
+    assert np.all(z.rejected == 0) and np.all(z.steps == z.steps[0]) and 10 <= z.steps[0] <= 13
+
+
+def test_full_size_adaptive_lorenz_properties():
+    # BASELINE configs[1] "fixed and adaptive step": 2^20 members; size-independent properties
+    n = 1 << 20
+    s = cases.lorenz(n=n, t1=50.0, arith="fast").stepsize(auto_stepsize(3)).run()
+    assert s.totals["kernel_kind"] == KERNEL_ODE_ADAPTIVE
+    assert s.totals["n_failed"] == 0
+    assert np.all(s.t == 50.0)
+    check_adaptive_counters(s, 7)
+    assert np.all(s.steps >= 500)  # h <= stepsize_range.end = 0.1
+    # on the attractor (rho in [20, 40]): bounded, z > 0
+    assert np.all(np.abs(s.p) < 100.0) and np.all(s.p[:, 2] > 0.0)
+    # same member integrated alone = same member integrated inside the ensemble (dynamic assignment
+    # of trajectories to lanes must not leak into results)
+    pick = np.array([0, 1, 31, 32, 4097, n // 2, n - 1])
+    rho = 20.0 + 20.0 * pick / (n - 1)
+    alone = cases.lorenz(n=len(pick), t1=50.0, arith="fast", rho=rho).stepsize(auto_stepsize(3)).run()
+    assert np.array_equal(alone.p, s.p[pick]) and np.array_equal(alone.steps, s.steps[pick])
+
 # ---------------------------------------------------------------- Lyapunov
 def test_lyapunov_scalar(oracle):
     lam = [-5., -4., -3., -2., -1., 1., 2., 3., 4., 5.]
@@ -510,6 +650,102 @@ def test_lyapunov_lorenz_fast_vs_strict_ensemble_mean():
     assert abs(lf.sum() + (10.0 + 1.0 + 8.0 / 3.0)) < 1e-6
     assert abs(lg.sum() + (10.0 + 1.0 + 8.0 / 3.0)) < 1e-6
 
+
+
+# ---------------------------------------------------------------- fixed step + Periodic callbacks (ode_fixed_periodic_kernel)
+KERNEL_ODE_FIXED_PERIODIC = 4
+
+
+def run_general(make):
+    os.environ["DFB_FORCE_GENERAL"] = "1"
+    try:
+        r = make().run()
+    finally:
+        del os.environ["DFB_FORCE_GENERAL"]
+    assert r.totals["kernel_kind"] == KERNEL_GENERAL
+    return r
+
+
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+def test_periodic_kernel_lyapunov_lorenz_equals_general_and_oracle(oracle, arith):
+    rho = np.linspace(20.0, 40.0, 77)   # 77: ragged warp
+    tmax = 20.0 if arith == "strict" else 5.0
+    mk = lambda: cases.lyap_lorenz(tmax, rho=rho, arith=arith)
+    hot = mk().run()
+    assert hot.totals["kernel_kind"] == KERNEL_ODE_FIXED_PERIODIC
+    gen = run_general(mk)
+    for a in ("steps", "events", "rhs_evals", "status", "rejected"):
+        assert np.array_equal(getattr(hot, a), getattr(gen, a)), a
+    assert np.array_equal(hot.t, gen.t)
+    if arith == "strict":
+        # same operation order in both kernels: bit-identical state and log sums
+        assert np.array_equal(hot.p, gen.p) and np.array_equal(hot.aux, gen.aux)
+        o = oracle.run_solver(mk(), n_threads=8)
+        assert_same_counters(hot, o)
+        assert np.array_equal(hot.p, o.p)                      # QR: sqrt and division are IEEE on both sides
+        assert np.max(np.abs(hot.aux - o.aux)) < 1e-9          # log() is within 1-2 ulp of glibc
+    else:
+        # FAST: pre-scaled rows + FMA vs the general kernel's contraction: rounding-level differences
+        # amplified by the chaotic flow (leading exponent up to ~1.4 at rho = 40: e^7 ~ 1e3 over t = 5)
+        assert np.max(np.abs(hot.p[:, :3] - gen.p[:, :3])) < 1e-9
+        assert np.max(np.abs(hot.aux - gen.aux)) < 1e-9
+
+
+def test_periodic_kernel_two_locators_and_event_log(oracle):
+    # two Periodic locators (different periods and an offset) + the event log; times coincide at
+    # t = 1.5, 3.0, ...: the strictly-earliest / lowest-index rule and DedupLocF decide who fires
+    lam = np.array([-1.0, -0.5, 0.25, 0.5]).reshape(-1, 1)
+
+    def mk():
+        return (d.Solver.new().initial(np.ones((4, 1))).interval(0.0, 7.0).stepsize(0.04)
+                .equation(d.systems.Linear1, lam)
+                .on_mut(d.Periodic(0.3, 0.0), "renormalize").on_mut(d.Periodic(0.5, 0.25), "renormalize")
+                .log_events(d.EventLog(64)))
+    hot = mk().run()
+    assert hot.totals["kernel_kind"] == KERNEL_ODE_FIXED_PERIODIC
+    o = oracle.run_solver(mk(), n_threads=2)
+    assert_same_counters(hot, o)
+    assert np.array_equal(hot.event_n, o.event_n)
+    ne = int(hot.event_n[0])
+    assert ne > 30
+    assert np.array_equal(hot.event_t[:, :ne], o.event_t[:, :ne])
+    assert np.array_equal(hot.event_index[:, :ne], o.event_index[:, :ne])
+    assert np.array_equal(hot.p, o.p) and np.array_equal(hot.t, o.t)
+    assert np.max(np.abs(hot.aux - o.aux)) < 1e-12
+    gen = run_general(mk)
+    assert np.array_equal(hot.p, gen.p) and np.array_equal(hot.aux, gen.aux)
+    assert np.array_equal(hot.event_t[:, :ne], gen.event_t[:, :ne])
+
+
+def test_periodic_kernel_stop_integration_is_per_lane(oracle):
+    # the egg-billiard reflection callback (examples/egg-billiard.rs:22-38) on a Periodic clock: member
+    # i calls stop_integration at its (i % 7 + 1)-th event, so lanes of one warp stop at different
+    # times while the rest of the warp keeps stepping
+    n = 70
+    max_refl = (np.arange(n) % 7 + 1).astype(np.float64).reshape(-1, 1)
+    phi = 2.0 * np.pi * np.arange(n) / n
+    y0 = np.stack([np.zeros(n), np.full(n, 0.1), 0.5 * np.cos(phi), 0.5 * np.sin(phi)], axis=1)
+
+    def mk():
+        return (d.Solver.new().initial(y0).interval(0.0, 5.0).stepsize(0.05)
+                .equation(d.systems.EggBilliard, max_refl).on_mut(d.Periodic(0.4, 0.0), "reflect"))
+    hot = mk().run()
+    assert hot.totals["kernel_kind"] == KERNEL_ODE_FIXED_PERIODIC
+    o = oracle.run_solver(mk(), n_threads=4)
+    assert_same_counters(hot, o)
+    assert np.all(hot.status == 64) and np.all(np.isinf(hot.t))       # DFB_TRAJ_STOPPED, t = +inf
+    assert np.array_equal(hot.events, (np.arange(n) % 7 + 1).astype(np.uint64))
+    assert np.array_equal(hot.p, o.p) and np.array_equal(hot.aux, o.aux)
+    gen = run_general(mk)
+    assert np.array_equal(hot.p, gen.p) and np.array_equal(hot.steps, gen.steps)
+
+
+def test_periodic_kernel_scalar_and_matrix_lyapunov_kinds():
+    # the reference's other Lyapunov tests also take the periodic kernel
+    assert cases.lyap_linear_1_const([-1.0, 2.0], 10.0).run().totals["kernel_kind"] == KERNEL_ODE_FIXED_PERIODIC
+    assert cases.lyap_linear_1_sin([-1.0, 2.0], 10.0).run().totals["kernel_kind"] == KERNEL_ODE_FIXED_PERIODIC
+    m = [cases.real_jordan_matrix([2., 0., -2.])]
+    assert cases.lyap_linear_3(m, 10.0).run().totals["kernel_kind"] == KERNEL_ODE_FIXED_PERIODIC
 
 # ---------------------------------------------------------------- full-size properties
 def test_full_size_lorenz_properties():

@@ -30,7 +30,7 @@ def timed(make, reps=2):
     ens.close()
     ms = float(np.mean(ms))
     return {"kernel_ms": ms, "steps": tot["steps"], "events": tot["events"], "rejected": tot["rejected"],
-            "rhs_evals": tot["rhs_evals"], "n_failed": tot["n_failed"],
+            "rhs_evals": tot["rhs_evals"], "n_failed": tot["n_failed"], "kernel_kind": tot["kernel_kind"],
             "steps_per_s": tot["steps"] / (ms * 1e-3), "events_per_s": tot["events"] / (ms * 1e-3)}
 
 

@@ -177,6 +177,53 @@ def dde_leg(d, torch, local_rank, K=3, W=2):
     }
 
 
+def other_config_legs(d, peak_tflops):
+    """The remaining BASELINE.json configs (parity-test cases, not the headline): one timed pass each
+    after one warm-up, kernel time from the library's CUDA events (dfb_totals.kernel_ms)."""
+    import cases
+    KIND = {0: "integrate_general_kernel", 1: "ode_fixed_kernel", 2: "dde_fixed_kernel",
+            3: "ode_adaptive_kernel", 4: "ode_fixed_periodic_kernel"}
+
+    def timed(make):
+        ens = make().build()
+        ens.run(); ens.synchronize()
+        ms = []
+        for _ in range(2):
+            ens.run(); ens.synchronize()
+            ms.append(ens.totals()["kernel_ms"])
+        tot = ens.totals()
+        ens.close()
+        m = float(np.mean(ms))
+        return {"kernel": KIND.get(tot["kernel_kind"], "?"), "kernel_ms": m, "rk_steps": tot["steps"],
+                "rejected": tot["rejected"], "events": tot["events"], "n_failed": tot["n_failed"],
+                "rk_steps_per_s": tot["steps"] / (m * 1e-3), "events_per_s": tot["events"] / (m * 1e-3)}
+
+    out = {}
+    auto = d.AutomaticStepsize(1e-2, (1e-6, 1e-1), [1e-9] * 3, [1e-9] * 3, 4, 0.9, (0.2, 5.0))
+    legs = {
+        # configs[1], adaptive half: 307 flop per ATTEMPTED step (SURVEY §8d: 252 + error estimate + controller)
+        "lorenz_2^20_adaptive_rktp64_tol1e-9": (lambda: cases.lorenz(n=1 << 20, t1=T_END, arith="fast").stepsize(auto), 307.0),
+        # configs[3]
+        "bouncing_ball_2^19_t=[0,8]": (lambda: cases.bouncing_ball(n=1 << 19, t1=8.0, arith="fast", events=0), None),
+        "egg_billiard_2^19_200_reflections": (lambda: cases.egg_billiard(n=1 << 19, reflections=200, arith="fast", events=0), None),
+        # configs[4]: Lorenz + 3x3 variational block (N = 12), QR every 0.5; flop/step by the same
+        # formula as the headline: 12(2*21+6) + 12*13 + 13 + 7*F_rhs, F_rhs = 8 + 45 + 1
+        "lyapunov_lorenz_2^18_rho_grid_t=[0,100]": (lambda: cases.lyap_lorenz(100.0, rho=np.linspace(20.0, 40.0, 1 << 18), arith="fast"), 1123.0),
+    }
+    for name, (mk, flops) in legs.items():
+        try:
+            r = timed(mk)
+            if flops:
+                att = r["rk_steps"] + r["rejected"]
+                r["algorithmic_flops_per_attempted_step"] = flops
+                r["achieved_tflops"] = flops * att / (r["kernel_ms"] * 1e-3) / 1e12
+                r["frac_of_fp64_peak"] = r["achieved_tflops"] / peak_tflops
+            out[name] = r
+        except Exception as e:  # the headline line must still print
+            out[name] = {"error": repr(e)}
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return 0
@@ -378,6 +425,13 @@ def main():
         except Exception as e:  # the headline line must still print
             secondary = {"error": repr(e)}
 
+    others = None
+    if world == 1 and not os.environ.get("DFB_BENCH_SKIP_OTHERS"):
+        try:
+            others = other_config_legs(d, peak)
+        except Exception as e:
+            others = {"error": repr(e)}
+
     line = {
         "metric": "rk_steps_per_sec", "value": value, "unit": "RK steps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": max_ms / K,
@@ -395,6 +449,7 @@ def main():
         "cpu_baseline": cpu_baseline,
         "wall_s_timed_region": t_wall,
         "secondary_dde": secondary,
+        "other_configs": others,
     }
     print(json.dumps(line))
     if world > 1:

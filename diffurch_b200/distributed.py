@@ -87,3 +87,56 @@ def run_sharded(make_solver, y0, params, rank, world, runner=None, group=None, d
             a = a.astype(np.int64)
         out[name] = all_gather_rows(a, group=group, device=device)
     return out
+
+
+class NcclComm:
+    """A raw ``ncclComm_t`` for `dfb_gather_final`, created with the NCCL that is already loaded in
+    the process (torch's bundled libnccl): rank 0 makes the unique id, torch.distributed broadcasts
+    it, every rank calls ``ncclCommInitRank``.  The C ABI takes the handle as ``void*``."""
+
+    def __init__(self, rank, world, group=None):
+        import ctypes as C
+        import glob
+        import os
+
+        import torch
+        import torch.distributed as dist
+
+        lib = None
+        for cand in (["libnccl.so.2"] +
+                     glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so*"))):
+            try:
+                lib = C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                break
+            except OSError:
+                continue
+        if lib is None:
+            raise RuntimeError("libnccl not found")
+
+        class UniqueId(C.Structure):
+            _fields_ = [("internal", C.c_char * 128)]  # NCCL_UNIQUE_ID_BYTES
+
+        self._lib = lib
+        uid = UniqueId()
+        if rank == 0:
+            rc = lib.ncclGetUniqueId(C.byref(uid))
+            if rc != 0:
+                raise RuntimeError(f"ncclGetUniqueId failed: {rc}")
+        raw = torch.frombuffer(bytearray(bytes(uid)), dtype=torch.uint8).clone()
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else None
+        t = raw.to(dev) if dev is not None else raw
+        dist.broadcast(t, src=0, group=group)
+        C.memmove(C.byref(uid), bytes(t.cpu().numpy().tobytes()), 128)
+        comm = C.c_void_p()
+        lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+        rc = lib.ncclCommInitRank(C.byref(comm), int(world), uid, int(rank))
+        if rc != 0:
+            raise RuntimeError(f"ncclCommInitRank failed: {rc}")
+        self.handle = comm
+        self.world = int(world)
+
+    def destroy(self):
+        if self.handle:
+            self._lib.ncclCommDestroy.argtypes = [__import__("ctypes").c_void_p]
+            self._lib.ncclCommDestroy(self.handle)
+            self.handle = None

@@ -57,22 +57,16 @@ def _worker(rank, world, port, n, out_path):
     lo = rank * m
     ens = make(y0[lo:lo + m], prm[lo:lo + m]).build()
     ens.run()
-    uid = [torch.cuda.nccl.unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)
-    capsule = torch._C._nccl_init_rank(world, uid[0], rank)
-    C.pythonapi.PyCapsule_GetName.restype = C.c_char_p
-    C.pythonapi.PyCapsule_GetName.argtypes = [C.py_object]
-    C.pythonapi.PyCapsule_GetPointer.restype = C.c_void_p
-    C.pythonapi.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
-    comm = C.pythonapi.PyCapsule_GetPointer(capsule, C.pythonapi.PyCapsule_GetName(capsule))
+    comm = dd.NcclComm(rank, world)
     t_all = np.empty(m * world)
     y_all = np.empty((m * world, 3))
     dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
-    rc = d.lib.dfb_gather_final(ens._h, C.c_void_p(comm), world, dp(t_all), dp(y_all), None)
+    rc = d.lib.dfb_gather_final(ens._h, comm.handle, world, dp(t_all), dp(y_all), None)
     assert rc == 0, d.lib.dfb_last_error()
     if rank == 0:
         np.savez(out_path, p=got["p"], t=got["t"], y_all=y_all, t_all=t_all)
     dist.barrier()
+    comm.destroy()
     dist.destroy_process_group()
 
 

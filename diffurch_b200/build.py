@@ -25,6 +25,7 @@ def _jobs():
     jobs = []
     for arith, tag, extra in ((0, "strict", ["-fmad=false"]), (1, "fast", [])):
         jobs.append(("kernels_ode_fixed.cu", f"ode_fixed_{tag}.o", [f"-DDFB_ARITH={arith}"] + extra))
+        jobs.append(("kernels_ode_event.cu", f"ode_event_{tag}.o", [f"-DDFB_ARITH={arith}"] + extra))
         for g in range(1, N_GROUPS + 1):
             jobs.append(("kernels_general.cu", f"general_g{g}_{tag}.o",
                          [f"-DDFB_ARITH={arith}", f"-DDFB_GROUP={g}"] + extra))

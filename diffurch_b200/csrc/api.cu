@@ -34,6 +34,14 @@ int run_ode_fixed_periodic_shim(int system_id, const dfb_tableau& rk, double t0,
                                 unsigned long long* events, unsigned long long* rhs_evals,
                                 uint32_t* status, int n_loc, const dfb_locator* loc, int event_capacity,
                                 double* ev_t, int32_t* ev_idx, uint32_t* n_events, cudaStream_t stream);
+int run_ode_event_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h, long long max_steps,
+                       size_t n, const double* y0, const double* params, double* t_final, double* y_final,
+                       double* aux_final, unsigned long long* steps, unsigned long long* events,
+                       unsigned long long* rhs_evals, uint32_t* status, int n_loc, const dfb_locator* loc,
+                       int event_capacity, double* ev_t, int32_t* ev_idx, uint32_t* n_events, int trace_every,
+                       int trace_capacity, double* trace_t, double* trace_y, uint32_t* n_samples,
+                       unsigned long long* queue, int locate_batch, int locate_wait, int n_sm,
+                       cudaStream_t stream);
 }
 namespace dfb_fast {
 int run_ode_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h,
@@ -46,6 +54,14 @@ int run_ode_fixed_periodic_shim(int system_id, const dfb_tableau& rk, double t0,
                                 unsigned long long* events, unsigned long long* rhs_evals,
                                 uint32_t* status, int n_loc, const dfb_locator* loc, int event_capacity,
                                 double* ev_t, int32_t* ev_idx, uint32_t* n_events, cudaStream_t stream);
+int run_ode_event_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h, long long max_steps,
+                       size_t n, const double* y0, const double* params, double* t_final, double* y_final,
+                       double* aux_final, unsigned long long* steps, unsigned long long* events,
+                       unsigned long long* rhs_evals, uint32_t* status, int n_loc, const dfb_locator* loc,
+                       int event_capacity, double* ev_t, int32_t* ev_idx, uint32_t* n_events, int trace_every,
+                       int trace_capacity, double* trace_t, double* trace_y, uint32_t* n_samples,
+                       unsigned long long* queue, int locate_batch, int locate_wait, int n_sm,
+                       cudaStream_t stream);
 }
 
 namespace dfb_fast {
@@ -581,6 +597,34 @@ int dfb_run(dfb_handle* h, void* stream_v) {
       h->launches = 1;
       h->used_hot_path = true;
       h->kernel_kind = DFB_KERNEL_ODE_FIXED_PERIODIC;
+      h->ran = true;
+      return DFB_OK;
+    }
+  }
+
+  // Fixed step + located events (dev/ode_event.cuh): state-function and Periodic locators, ODE only.
+  bool event_eligible = p.stepsize_kind == DFB_STEP_FIXED && p.n_loc > 0 && !h->info.uses_history &&
+                        p.history_id == DFB_HIST_CONSTANT && !std::getenv("DFB_FORCE_GENERAL");
+  for (int l = 0; l < p.n_loc && event_eligible; ++l)
+    event_eligible = p.loc[l].kind == DFB_LOC_STATEFN || p.loc[l].kind == DFB_LOC_PERIODIC;
+  if (event_eligible) {
+    DFB_CUDA(cudaMemsetAsync(h->d_rejected, 0, n * sizeof(unsigned long long), stream));
+    DFB_CUDA(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned long long), stream));
+    DFB_CUDA(cudaEventRecord(h->ev0, stream));
+    auto shim = p.arith == DFB_ARITH_FAST ? dfb_fast::run_ode_event_shim : dfb_strict::run_ode_event_shim;
+    const bool tracing = h->d_trace_t && p.trace_every > 0;
+    const int rc = shim(p.system_id, p.rk, p.t0, p.t1, p.h, p.max_steps, n, y0, params, h->d_t, h->d_y,
+                        h->info.n_aux ? h->d_aux : nullptr, h->d_steps, h->d_events, h->d_rhs, h->d_status,
+                        p.n_loc, p.loc, p.event_capacity, h->d_ev_t, h->d_ev_idx, h->d_nevents,
+                        tracing ? p.trace_every : 0, p.trace_capacity, tracing ? h->d_trace_t : nullptr,
+                        h->d_trace_y, h->d_nsamples, h->d_queue, h->locate_batch, h->locate_max_wait, h->n_sm,
+                        stream);
+    if (rc > 0) return fail(DFB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(cudaError_t(rc)));
+    if (rc == 0) {
+      DFB_CUDA(cudaEventRecord(h->ev1, stream));
+      h->launches = 1;
+      h->used_hot_path = true;
+      h->kernel_kind = DFB_KERNEL_ODE_EVENT;
       h->ran = true;
       return DFB_OK;
     }

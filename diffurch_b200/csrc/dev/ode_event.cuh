@@ -1,0 +1,436 @@
+// Hot path #3: fixed-step explicit RK over an ODE ensemble WITH located events (reference:
+// Solver::run solver.rs:292-310; Detect/Locate, detection and location methods, Periodic,
+// filters, LocCallback, HListLocateEarliest, DedupLocF — loc.rs:11-80, 127-143, 200-335,
+// 465-700, 795-883, 970-1052; State::{make_step, commit_step, make_zero_step, undo_step}
+// state.rs:94-150).  BASELINE configs[3]: bouncing ball, egg billiard.
+//
+// Same semantics as the general integrator (integrator.cuh) for the ODE + state-function /
+// Periodic locator subset, but built like the hot-path kernels:
+//
+//  * the whole State and every locator's bookkeeping live in registers: the locator loops are
+//    unrolled over a compile-time locator count, so nothing is indexed at run time (the general
+//    kernel keeps that state in local memory: 39 % LSU-pipe utilisation on the bouncing ball);
+//  * ONE make_step call site: lanes taking an ordinary step and lanes re-taking a step truncated
+//    to an event time run the same instructions (the step length is per lane);
+//  * warp-level batching of event location: a lane that detects an event parks; the warp votes
+//    and runs the ~45-iteration bisections together once enough lanes are parked (or the first
+//    one has waited long enough, or nobody can advance), so diverging lanes do not serialise the
+//    warp on every step;
+//  * FAST arithmetic only: the step's interpolant is pre-combined ONCE per located event into
+//    polynomial coefficients  y(theta) = p_prev + sum_j c_j theta^j,  c_j = h sum_i k_i bi[i][j],
+//    so a bisection iteration is an (I-1)-term Horner chain per component instead of the
+//    reference's S x I sums (rk.rs:24-47), and the derivative interpolant is skipped for
+//    detectors that never read `s.d`.  STRICT keeps the reference's dense_output and its
+//    operation order: bit-identical event times;
+//  * dynamic trajectory assignment (global work counter) as in ode_adaptive.cuh: members stop at
+//    different times (egg billiard: after 200 reflections), finished lanes pull the next member.
+#pragma once
+#include "common.cuh"
+#include "integrator.cuh"
+#include "ode_fixed.cuh"
+#include "systems.cuh"
+
+namespace DFB_NS {
+
+template <class Sys, int S_, int I_, unsigned long long AMASK, unsigned BMASK, bool FAST, int NLOC>
+struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
+  using Base = OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1>;
+  static constexpr int S = S_, I = I_;
+  static_assert(!Sys::reads_d, "views of this kernel carry the fresh k[0] where the reference carries the stale d");
+  static constexpr int N = Sys::N;
+  static constexpr int NA = Sys::NA > 0 ? Sys::NA : 1;
+  using Ref = StateRef<N, NoHist>;
+  using RefMut = StateRefMut<N, NoHist>;
+  struct Tab {  // the continuous-extension rows of the argument block, for dense_output<D, N>
+    static constexpr int S = S_, I = I_;
+    const double* v;
+    __device__ __forceinline__ double bi(int i, int j) const { return v[i * DFB_MAX_INTERP + j]; }
+  };
+  using Base::A;
+  using Base::t_curr;
+  using Base::t_prev;
+
+  // slot 0 of the base's [TPT = 1] arrays
+  __device__ __forceinline__ double* p_curr() { return Base::p_curr[0]; }
+  __device__ __forceinline__ double* p_prev() { return Base::p_prev[0]; }
+  __device__ __forceinline__ double* d_curr() { return Base::d_curr[0]; }
+  __device__ __forceinline__ double* prm() { return Base::prm[0]; }
+  __device__ __forceinline__ double (*k())[N] { return Base::k[0]; }  // k()[0] = d_prev after a step
+
+  size_t gid;
+  double aux[NA];
+  double cj[I > 1 ? I - 1 : 1][N];  // FAST: pre-combined interpolant of the parked step
+  double last_call[NLOC], sep_prev[NLOC];
+  int every_i[NLOC];
+  uint32_t has_last_call, status;
+  unsigned n_steps, n_events, n_evlog, n_samples;
+  unsigned long long n_rhs, on_step_calls;
+
+  __device__ explicit OdeEventStepper(const OdeFixedArgs& A_) : Base(A_) {}
+
+  __device__ __forceinline__ Ref view_curr() {
+    return Ref{t_curr, p_curr(), d_curr(), t_prev, p_prev(), &this->nohist};
+  }
+  __device__ __forceinline__ Ref view_prev() {  // state_fn.rs:181-188; d_prev is still in k[0]
+    return Ref{t_prev, p_prev(), k()[0], t_prev, p_prev(), &this->nohist};
+  }
+
+  // ---- interpolant of the step in flight (State::eval, state.rs:83-92) ------------------
+  __device__ __forceinline__ void precombine() {
+    if (!FAST) return;
+    const double t_step = t_curr - t_prev;
+#pragma unroll
+    for (int j = 1; j < I; ++j)
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < S; ++i) acc = fma(k()[i][n], A.bi[i * DFB_MAX_INTERP + j], acc);
+        cj[j - 1][n] = acc * t_step;
+      }
+  }
+  template <int D>
+  __device__ __forceinline__ void eval_in_step(double t, double* out) {
+    const double t_step = t_curr - t_prev;
+    const double theta = (t - t_prev) / t_step;
+    if (FAST && D == 0) {
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        double acc = cj[I - 2][n];
+#pragma unroll
+        for (int j = I - 3; j >= 0; --j) acc = fma(acc, theta, cj[j][n]);
+        out[n] = fma(acc, theta, p_prev()[n]);
+      }
+    } else {
+      dense_output<D, N>(Tab{A.bi}, p_prev(), t_step, theta, k(), out);
+    }
+  }
+
+  // EvalState of locator L's function: which = 0 eval_curr, 1 eval_prev, 2 eval_at(t)
+  __device__ __forceinline__ double loc_fn(const dfb_locator& L, int which, double t) {
+    if (L.detection == DFB_DET_STEP) return 1.0;
+    if (which == 0) return Sys::detector(L.detector_id, view_curr(), prm());
+    if (which == 1) return Sys::detector(L.detector_id, view_prev(), prm());
+    double y[N], dy[N];
+    eval_in_step<0>(t, y);
+    if (Sys::reads_d) eval_in_step<1>(t, dy);  // state_fn.rs:190-201 builds both; only `d` readers need it
+    return Sys::detector(L.detector_id, Ref{t, y, Sys::reads_d ? dy : y, t, y, &this->nohist}, prm());
+  }
+
+  // detection_method (loc.rs:127-143), Periodic::detect (:318-322)
+  __device__ __forceinline__ bool detect_base(const dfb_locator& L) {
+    if (L.kind == DFB_LOC_PERIODIC) {
+      const double prev = floor((t_prev - L.offset) / L.period);
+      const double curr = floor((t_curr - L.offset) / L.period);
+      return prev < curr;
+    }
+    const int det = L.detection;
+    if (det == DFB_DET_STEP) return true;
+    const bool needs_prev = det == DFB_DET_ZERO || det == DFB_DET_ABOVE_ZERO || det == DFB_DET_BELOW_ZERO ||
+                            det == DFB_DET_SWITCH || det == DFB_DET_SWITCH_TRUE || det == DFB_DET_SWITCH_FALSE;
+    const double c = loc_fn(L, 0, 0.0);
+    const double p = needs_prev ? loc_fn(L, 1, 0.0) : 0.0;
+    const bool cb = c != 0.0, pb = p != 0.0;
+    switch (det) {
+      case DFB_DET_ZERO: return (c > 0.0 && p <= 0.0) || (c <= 0.0 && p > 0.0);
+      case DFB_DET_ABOVE_ZERO: return c > 0.0 && p <= 0.0;
+      case DFB_DET_BELOW_ZERO: return c < 0.0 && p >= 0.0;
+      case DFB_DET_POSITIVE: return c >= 0.0;
+      case DFB_DET_NEGATIVE: return c <= 0.0;
+      case DFB_DET_SWITCH: return cb != pb;
+      case DFB_DET_SWITCH_TRUE: return cb && !pb;
+      case DFB_DET_SWITCH_FALSE: return !cb && pb;
+      case DFB_DET_IS_TRUE: return cb;
+      case DFB_DET_IS_FALSE: return !cb;
+    }
+    return false;
+  }
+
+  // location_method (loc.rs:200-285), Periodic::locate (:332-334)
+  __device__ double locate_base(const dfb_locator& L) {
+    if (L.kind == DFB_LOC_PERIODIC) return floor((t_curr - L.offset) / L.period) * L.period + L.offset;
+    const int location = L.location;
+    if (location == DFB_LOCATE_STEP_BEGIN) return t_prev;
+    if (location == DFB_LOCATE_STEP_END) return t_curr;
+    if (location == DFB_LOCATE_STEP_MIDDLE) return 0.5 * (t_curr - t_prev);  // sic (loc.rs:202-204)
+    const bool is_bool = location == DFB_LOCATE_BISECTION_BOOL;
+    const double fc = is_bool ? 0.0 : loc_fn(L, 0, 0.0);
+    const double fp = (is_bool || location == DFB_LOCATE_LERP) ? loc_fn(L, 1, 0.0) : 0.0;
+    if (location == DFB_LOCATE_LERP) return (fc * t_prev - fp * t_curr) / (fc - fp);
+    double lft = t_prev, rgt = t_curr;
+    if (is_bool ? (fp != 0.0) : (fc < 0.0)) {
+      const double tmp = lft;
+      lft = rgt;
+      rgt = tmp;
+    }
+    double w = fabs(rgt - lft);
+    double w_prev = 2.0 * w;
+    if (location == DFB_LOCATE_REGULA_FALSI) {
+      while (w < w_prev) {
+        w_prev = w;
+        double fv[3];
+        double m = 0.0;
+#pragma unroll 1
+        for (int q = 0; q < 3; ++q) {
+          if (q == 2) m = (fv[1] * lft - fv[0] * rgt) / (fv[1] - fv[0]);
+          fv[q] = loc_fn(L, 2, q == 0 ? lft : (q == 1 ? rgt : m));
+        }
+        if (fv[2] < 0.0) rgt = m;
+        else lft = m;
+        w = fabs(rgt - lft);
+      }
+      return fmax(lft, rgt);
+    }
+    // Bisection (loc.rs:235-259) / BisectionBool (:210-234)
+    double m = 0.5 * (lft + rgt);
+#pragma unroll 1
+    while (w < w_prev) {
+      w_prev = w;
+      const double f = loc_fn(L, 2, m);
+      const bool go_left = is_bool ? !(f != 0.0) : (f < 0.0);
+      if (go_left) lft = m;
+      else rgt = m;
+      m = 0.5 * (lft + rgt);
+      w = fabs(rgt - lft);
+    }
+    return fmax(lft, rgt);
+  }
+
+  // Filter state machines (loc.rs:613-688); l is a compile-time index after unrolling
+  __device__ __forceinline__ bool filter_pass(const dfb_locator& L, int l, double t) {
+    switch (L.filter) {
+      case DFB_FILTER_EVERY:
+        every_i[l] += 1;
+        if (every_i[l] >= L.filter_n) {
+          every_i[l] = 0;
+          return true;
+        }
+        return false;
+      case DFB_FILTER_SEPARATED_BY:
+        if (t >= sep_prev[l] + L.filter_a) {
+          sep_prev[l] = t;
+          return true;
+        }
+        return false;
+      case DFB_FILTER_IN_INTERVAL: return t >= L.filter_a && t < L.filter_b;
+    }
+    return true;
+  }
+
+  // DedupLocF (loc.rs:1002-1011) + filter wrappers (FilterAfterDetection :484-486, FilterLocated :568-576)
+  __device__ __forceinline__ bool detect_phase(const dfb_locator& L, int l) {
+    if (L.dedup && ((has_last_call >> l) & 1u) && !(t_prev > last_call[l])) return false;
+    if (!detect_base(L)) return false;
+    if (L.filter == DFB_FILTER_SEPARATED_BY || L.filter == DFB_FILTER_IN_INTERVAL) {
+      precombine();  // FilterLocated::detect locates at once (rare: filtered locators only)
+      return filter_pass(L, l, locate_base(L));
+    }
+    if (L.filter == DFB_FILTER_EVERY) return filter_pass(L, l, t_curr);
+    return true;
+  }
+
+  // output policy standing in for on_step closures (solver.rs:290, 309)
+  __device__ __forceinline__ void on_step() {
+    if (A.trace_every > 0) {
+      if (on_step_calls % (unsigned long long)A.trace_every == 0 && n_samples < uint32_t(A.trace_capacity)) {
+        const size_t n_traj = A.n_traj;
+        A.trace_t[size_t(n_samples) * n_traj + gid] = t_curr;
+#pragma unroll
+        for (int n = 0; n < N; ++n) A.trace_y[(size_t(n_samples) * N + n) * n_traj + gid] = p_curr()[n];
+        ++n_samples;
+      }
+      ++on_step_calls;
+    }
+  }
+
+  __device__ __forceinline__ int next_mode() {
+    if (A.max_steps > 0 && (long long)n_steps >= A.max_steps && t_curr < A.t1) {
+      status |= DFB_TRAJ_STEP_LIMIT;
+      return MODE_DONE;
+    }
+    return (t_curr < A.t1) ? MODE_STEP : MODE_DONE;
+  }
+
+  // pull the next member; returns MODE_DONE when the ensemble is exhausted
+  __device__ int fetch(bool* exhausted) {
+    const unsigned long long i = atomicAdd(A.queue, 1ull);
+    if (i >= A.n_traj) {
+      *exhausted = true;
+      return MODE_DONE;
+    }
+    gid = size_t(i);
+    const size_t n_traj = A.n_traj;
+#pragma unroll
+    for (int n = 0; n < Sys::NP; ++n) prm()[n] = A.params[size_t(n) * n_traj + i];
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      p_curr()[n] = p_prev()[n] = A.y0[size_t(n) * n_traj + i];
+      d_curr()[n] = 0.0;
+      k()[0][n] = 0.0;
+    }
+#pragma unroll
+    for (int n = 0; n < NA; ++n) aux[n] = 0.0;
+    t_curr = t_prev = A.t0;
+    has_last_call = 0u;
+    status = 0u;
+#pragma unroll
+    for (int l = 0; l < NLOC; ++l) {
+      last_call[l] = 0.0;
+      every_i[l] = l < A.n_loc ? A.loc[l].filter_n - 1 : 0;
+      sep_prev[l] = -1.7976931348623157e308;  // T::min_value()
+    }
+    n_steps = n_events = n_evlog = n_samples = 0u;
+    n_rhs = on_step_calls = 0ull;
+    on_step();  // events_on_step at t_init (solver.rs:290)
+    return next_mode();
+  }
+
+  __device__ void store() {
+    const size_t n_traj = A.n_traj;
+    uint32_t st = status;
+    if (t_curr == dev_inf()) st |= DFB_TRAJ_STOPPED;
+    bool finite = true;
+#pragma unroll
+    for (int n = 0; n < N; ++n) finite = finite && (fabs(p_curr()[n]) < dev_inf());
+    if (!finite) st |= DFB_TRAJ_NONFINITE;
+    A.t_final[gid] = t_curr;
+#pragma unroll
+    for (int n = 0; n < N; ++n) A.y_final[size_t(n) * n_traj + gid] = p_curr()[n];
+    if (A.aux_final) {
+#pragma unroll
+      for (int n = 0; n < Sys::NA; ++n) A.aux_final[size_t(n) * n_traj + gid] = aux[n];
+    }
+    A.steps[gid] = n_steps;
+    A.events[gid] = n_events;
+    A.rhs_evals[gid] = n_rhs;
+    A.status[gid] = st;
+    if (A.n_events) A.n_events[gid] = n_evlog;
+    if (A.n_samples) A.n_samples[gid] = n_samples;
+  }
+
+  // ---- Solver::run (solver.rs:275-313) as a warp-friendly state machine ------------------
+  __device__ void run() {
+    int mode = MODE_DONE;
+    bool have = false, exhausted = false;
+    double ev_time = 0.0;
+    int ev_index = 0;
+    uint32_t fired_mask = 0u;
+    int parked_iters = 0;  // warp-uniform: step rounds since the first lane parked
+
+    while (true) {
+      // finished lanes hand in their member and pull the next one
+      while (mode == MODE_DONE && !exhausted) {
+        if (have) store();
+        mode = fetch(&exhausted);
+        have = !exhausted;
+      }
+      const unsigned stepping = __ballot_sync(0xffffffffu, mode == MODE_STEP || mode == MODE_EVENT_RESTEP);
+      const unsigned parked = __ballot_sync(0xffffffffu, mode == MODE_LOCATE);
+      if (stepping == 0u && parked == 0u) break;  // every lane is done and the ensemble is exhausted
+
+      // (1) batched event location (HListLocateEarliest, loc.rs:821-835)
+      if (parked != 0u && (stepping == 0u || __popc(parked) >= A.locate_batch || parked_iters >= A.locate_wait)) {
+        parked_iters = 0;
+        if (mode == MODE_LOCATE) {
+          precombine();
+          bool found = false;
+          double best_t = 0.0;
+          int best_i = 0;
+#pragma unroll
+          for (int l = 0; l < NLOC; ++l) {
+            if (l < A.n_loc && ((fired_mask >> l) & 1u)) {
+              const double tl = locate_base(A.loc[l]);
+              if (!found || tl < best_t) {  // strictly earliest, first index wins ties
+                found = true;
+                best_t = tl;
+                best_i = l;
+              }
+            }
+          }
+          if (found && best_t >= t_prev) {  // solver.rs:299-300
+            // undo_step (state.rs:146-150)
+            t_curr = t_prev;
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+              p_curr()[n] = p_prev()[n];
+              d_curr()[n] = k()[0][n];
+            }
+            ev_time = best_t;
+            ev_index = best_i;
+            mode = MODE_EVENT_RESTEP;
+          } else {
+            ++n_steps;  // commit_step
+            on_step();
+            mode = next_mode();
+          }
+        }
+        continue;
+      }
+      if (parked != 0u) ++parked_iters;
+
+      // (2) one make_step for every lane that can advance
+      if (mode == MODE_STEP || mode == MODE_EVENT_RESTEP) {
+        const bool restep = mode == MODE_EVENT_RESTEP;
+        const double h_req = restep ? (ev_time - t_curr) : fmin(A.h, A.t1 - t_curr);
+        if (t_prev == t_curr) {  // state.rs:97-98: make_step evaluates k[0] itself
+          Sys::rhs(view_curr(), prm(), d_curr());
+          ++n_rhs;
+        }
+        this->template step<false>(h_req);
+        n_rhs += S;
+        if (restep) {
+          // solver.rs:304-309: commit; zero step; callback of the located event; commit
+          t_prev = t_curr;
+#pragma unroll
+          for (int n = 0; n < N; ++n) p_prev()[n] = p_curr()[n];
+#pragma unroll
+          for (int l = 0; l < NLOC; ++l) {
+            if (l == ev_index) {
+              const dfb_locator& L = A.loc[l];
+              if (L.dedup) {  // DedupLocF::eval_mut (loc.rs:1023-1026)
+                has_last_call |= 1u << l;
+                last_call[l] = t_curr;
+              }
+              if (L.callback_id != DFB_CB_NONE) {
+                RefMut m{&t_curr, p_curr(), d_curr(), t_prev, p_prev(), &this->nohist};
+                Sys::callback(L.callback_id, m, prm(), aux);
+              }
+            }
+          }
+          ++n_events;
+          if (A.event_capacity > 0) {
+            if (n_evlog < uint32_t(A.event_capacity)) {
+              A.ev_t[size_t(n_evlog) * A.n_traj + gid] = ev_time;
+              A.ev_idx[size_t(n_evlog) * A.n_traj + gid] = ev_index;
+            }
+            ++n_evlog;
+          }
+          ++n_steps;
+          on_step();
+          mode = next_mode();
+        } else {
+          fired_mask = 0u;
+#pragma unroll
+          for (int l = 0; l < NLOC; ++l)
+            if (l < A.n_loc && detect_phase(A.loc[l], l)) fired_mask |= 1u << l;
+          if (fired_mask != 0u) {
+            mode = MODE_LOCATE;
+          } else {
+            ++n_steps;  // commit_step
+            on_step();
+            mode = next_mode();
+          }
+        }
+      }
+    }
+  }
+};
+
+template <class Sys, int S, int I, unsigned long long AMASK, unsigned BMASK, bool FAST, int NLOC, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+    ode_event_kernel(const __grid_constant__ OdeFixedArgs A) {
+  OdeEventStepper<Sys, S, I, AMASK, BMASK, FAST, NLOC> st(A);
+  st.run();
+}
+
+}  // namespace DFB_NS

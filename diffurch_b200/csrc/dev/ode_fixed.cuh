@@ -48,6 +48,15 @@ struct OdeFixedArgs {
   double* ev_t;                  // [ecap][n]
   int32_t* ev_idx;               // [ecap][n]
   uint32_t* n_events;            // [n]
+  // ---- state-function events (ode_event_kernel, dev/ode_event.cuh)
+  double bi[DFB_MAX_STAGES * DFB_MAX_INTERP];  // continuous extension (rk.rs:13)
+  long long max_steps;
+  unsigned long long* queue;     // work counter (zeroed before the launch)
+  int32_t locate_batch, locate_wait;
+  int32_t trace_every, trace_capacity;
+  double* trace_t;               // [cap][n]
+  double* trace_y;               // [cap][N][n]
+  uint32_t* n_samples;           // [n]
 };
 
 __host__ __device__ constexpr unsigned long long amask_bit(int i, int j) { return 1ull << (i * 8 + j); }

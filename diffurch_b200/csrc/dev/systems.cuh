@@ -134,6 +134,8 @@ struct SysBase {
   static constexpr bool uses_history = false;
   // rhs depends on (t, p, params) only: not on the stale d, p_prev/t_prev or the history
   static constexpr bool pure_rhs = true;
+  // no functor of the system (rhs, detectors, callbacks) reads the view's `d` (state_fn.rs:17)
+  static constexpr bool reads_d = false;
   template <class V>
   __device__ static double detector(int, const V&, const double*) { return 0.0; }
   template <class M>

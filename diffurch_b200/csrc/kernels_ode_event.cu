@@ -1,0 +1,110 @@
+// Instantiations + launcher of the fixed-step ODE + located-events kernel (dev/ode_event.cuh).
+// Compiled twice (see dev/common.cuh): STRICT (reference dense output, bit-identical event
+// times) and FAST (pre-combined interpolant).
+#include "dev/ode_event.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+namespace DFB_NS {
+namespace {
+constexpr int kBlock = 128;
+constexpr bool kFast = (DFB_ARITH == 1);
+
+template <class Kernel>
+void launch_grid(Kernel kernel, const OdeFixedArgs& A, int n_sm, cudaStream_t stream) {
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0);
+  const size_t want = (A.n_traj + kBlock - 1) / kBlock;
+  const size_t grid = std::min(want, size_t(per_sm > 0 ? per_sm : 1) * size_t(n_sm > 0 ? n_sm : 1));
+  kernel<<<unsigned(grid ? grid : 1), kBlock, 0, stream>>>(A);
+}
+
+template <class Sys, int S, int I>
+bool try_launch(int S_rt, int I_rt, const OdeFixedArgs& A, int n_sm, cudaStream_t stream, int* rc) {
+  if (S_rt != S || I_rt != I) return false;
+  constexpr unsigned long long AM = amask_full_lower(S);
+  constexpr unsigned BM = (1u << S) - 1u;
+  if (A.n_loc <= 1) launch_grid(ode_event_kernel<Sys, S, I, AM, BM, kFast, 1, kBlock>, A, n_sm, stream);
+  else if (A.n_loc == 2) launch_grid(ode_event_kernel<Sys, S, I, AM, BM, kFast, 2, kBlock>, A, n_sm, stream);
+  else launch_grid(ode_event_kernel<Sys, S, I, AM, BM, kFast, DFB_MAX_LOCATORS, kBlock>, A, n_sm, stream);
+  *rc = int(cudaGetLastError());
+  return true;
+}
+}  // namespace
+
+// returns 0 = launched, >0 = CUDA error code, -1 = no compiled kernel for this combination.
+// `A` comes pre-filled by fill_event_args (kernels_ode_fixed.cu shares the argument block).
+int launch_ode_event(int system_id, int S, int I, const OdeFixedArgs& A, int n_sm, cudaStream_t stream) {
+  int rc = 0;
+  bool ok = false;
+  switch (system_id) {
+    case DFB_SYS_BOUNCING_BALL:
+      ok = try_launch<SysBouncingBall, 7, 5>(S, I, A, n_sm, stream, &rc) ||
+           try_launch<SysBouncingBall, 5, 4>(S, I, A, n_sm, stream, &rc) ||
+           try_launch<SysBouncingBall, 4, 2>(S, I, A, n_sm, stream, &rc);
+      break;
+    case DFB_SYS_EGG_BILLIARD: ok = try_launch<SysEggBilliard, 7, 5>(S, I, A, n_sm, stream, &rc); break;
+    case DFB_SYS_RELAY_MSIGN:
+      ok = try_launch<SysRelayMsign, 7, 5>(S, I, A, n_sm, stream, &rc) ||
+           try_launch<SysRelayMsign, 4, 2>(S, I, A, n_sm, stream, &rc);
+      break;
+    case DFB_SYS_LINEAR3: ok = try_launch<SysLinear3, 7, 5>(S, I, A, n_sm, stream, &rc); break;
+    case DFB_SYS_HARMONIC: ok = try_launch<SysHarmonic, 7, 5>(S, I, A, n_sm, stream, &rc); break;
+    default: break;
+  }
+  return ok ? rc : -1;
+}
+
+int run_ode_event_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h, long long max_steps,
+                       size_t n, const double* y0, const double* params, double* t_final, double* y_final,
+                       double* aux_final, unsigned long long* steps, unsigned long long* events,
+                       unsigned long long* rhs_evals, uint32_t* status, int n_loc, const dfb_locator* loc,
+                       int event_capacity, double* ev_t, int32_t* ev_idx, uint32_t* n_events, int trace_every,
+                       int trace_capacity, double* trace_t, double* trace_y, uint32_t* n_samples,
+                       unsigned long long* queue, int locate_batch, int locate_wait, int n_sm,
+                       cudaStream_t stream) {
+  OdeFixedArgs A;
+  std::memset(&A, 0, sizeof(A));
+  for (int i = 0; i < DFB_MAX_STAGES; ++i) {
+    for (int j = 0; j < DFB_MAX_STAGES; ++j) A.a[i * DFB_MAX_STAGES + j] = rk.a[i * DFB_MAX_STAGES + j];
+    A.b[i] = rk.b[i];
+    A.c[i] = rk.c[i];
+    for (int j = 0; j < DFB_MAX_INTERP; ++j) {
+      A.bi[i * DFB_MAX_INTERP + j] = rk.bi[i * DFB_MAX_INTERP + j];
+      // the FAST interpolant is p_prev + sum_{j>=1} c_j theta^j: needs b_i(0) = 0 (true of every rk.rs tableau)
+      if (kFast && j == 0 && i < rk.S && rk.bi[i * DFB_MAX_INTERP] != 0.0) return -1;
+    }
+  }
+  A.t0 = t0;
+  A.t1 = t1;
+  A.h = h;
+  A.max_steps = max_steps;
+  A.n_traj = n;
+  A.y0 = y0;
+  A.params = params;
+  A.t_final = t_final;
+  A.y_final = y_final;
+  A.aux_final = aux_final;
+  A.steps = steps;
+  A.events = events;
+  A.rhs_evals = rhs_evals;
+  A.status = status;
+  A.n_loc = n_loc;
+  for (int l = 0; l < n_loc && l < DFB_MAX_LOCATORS; ++l) A.loc[l] = loc[l];
+  A.event_capacity = ev_t ? event_capacity : 0;
+  A.ev_t = ev_t;
+  A.ev_idx = ev_idx;
+  A.n_events = n_events;
+  A.trace_every = trace_t ? trace_every : 0;
+  A.trace_capacity = trace_capacity;
+  A.trace_t = trace_t;
+  A.trace_y = trace_y;
+  A.n_samples = n_samples;
+  A.queue = queue;
+  A.locate_batch = locate_batch;
+  A.locate_wait = locate_wait;
+  return launch_ode_event(system_id, rk.S, rk.I, A, n_sm, stream);
+}
+
+}  // namespace DFB_NS

@@ -310,8 +310,10 @@ typedef enum dfb_kernel_kind {
   DFB_KERNEL_ODE_FIXED = 1,    /* ode_fixed_kernel: fixed step, registers only */
   DFB_KERNEL_DDE_FIXED = 2,    /* dde_fixed_kernel: constant delay, coefficient ring */
   DFB_KERNEL_ODE_ADAPTIVE = 3, /* ode_adaptive_kernel: AutomaticStepsize, dynamic trajectory queue */
-  DFB_KERNEL_ODE_FIXED_PERIODIC = 4 /* ode_fixed_periodic_kernel: fixed step + Periodic callbacks
-                                       (warp-uniform event handling; the Lyapunov-batch shape) */
+  DFB_KERNEL_ODE_FIXED_PERIODIC = 4, /* ode_fixed_periodic_kernel: fixed step + Periodic callbacks
+                                        (warp-uniform event handling; the Lyapunov-batch shape) */
+  DFB_KERNEL_ODE_EVENT = 5          /* ode_event_kernel: fixed step + located state-function events
+                                       (register-resident locators, warp-batched bisection) */
 } dfb_kernel_kind;
 
 /* Solver::new + setters -> one handle for `n_traj` trajectories on `device`. */

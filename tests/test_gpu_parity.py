@@ -25,6 +25,17 @@ def run_both(oracle, make, **kw):
     return g, o
 
 
+KERNEL_GENERAL, KERNEL_ODE_FIXED, KERNEL_DDE_FIXED, KERNEL_ODE_ADAPTIVE = 0, 1, 2, 3
+def run_general(make):
+    os.environ["DFB_FORCE_GENERAL"] = "1"
+    try:
+        r = make().run()
+    finally:
+        del os.environ["DFB_FORCE_GENERAL"]
+    assert r.totals["kernel_kind"] == KERNEL_GENERAL
+    return r
+
+
 def assert_same_trace(g, o, exact=True, rtol=0.0, atol=0.0):
     assert np.array_equal(g.trace_n, o.trace_n)
     for i in range(len(g.trace_n)):
@@ -260,6 +271,86 @@ def test_filters_every_separated_in_interval(oracle):
         assert g.event_n[0] > 0
 
 
+
+# ---------------------------------------------------------------- fixed step + located events (ode_event_kernel)
+KERNEL_ODE_EVENT = 5
+
+
+def _same_everything(a, b):
+    for name in ("t", "p", "aux", "steps", "events", "rhs_evals", "status", "rejected"):
+        x, y = getattr(a, name), getattr(b, name)
+        if x is not None and np.size(x):
+            assert np.array_equal(x, y, equal_nan=True), name
+    if a.event_n is not None:
+        assert np.array_equal(a.event_n, b.event_n)
+        assert np.array_equal(a.event_t, b.event_t) and np.array_equal(a.event_index, b.event_index)
+    if a.trace_n is not None:
+        assert_same_trace(a, b, exact=True)
+
+
+@pytest.mark.parametrize("case", ["bouncing_ball", "egg_billiard", "relay_msign", "fibonacci"])
+def test_event_kernel_strict_equals_general_kernel_and_oracle(oracle, case):
+    mk = {"bouncing_ball": lambda: cases.bouncing_ball(n=96, t1=8.0, trace=d.Trace(1, 2048)),
+          "egg_billiard": lambda: cases.egg_billiard(n=64, reflections=60),
+          "relay_msign": cases.relay_msign, "fibonacci": cases.fibonacci}[case]
+    hot = mk().run()
+    assert hot.totals["kernel_kind"] == KERNEL_ODE_EVENT
+    gen = run_general(mk)
+    _same_everything(hot, gen)
+    o = oracle.run_solver(mk(), n_threads=8)
+    assert_same_counters(hot, o)
+    assert np.array_equal(hot.event_t, o.event_t) and np.array_equal(hot.p, o.p)
+
+
+def test_event_kernel_dynamic_assignment_ragged_costs(oracle):
+    # members stop after very different numbers of reflections (1 .. 97), far more members than one
+    # block: lanes hand in finished members and pull new ones from the work counter; results are
+    # indexed by member and must not depend on which lane integrated what
+    n = 3001
+    refl = (np.arange(n) * 7 % 97 + 1).astype(np.float64)
+
+    def mk(arith="strict"):
+        return _egg_with_reflections(n, refl, arith)
+    hot = mk().run()
+    assert hot.totals["kernel_kind"] == KERNEL_ODE_EVENT
+    assert np.array_equal(hot.events, refl.astype(np.uint64)) and np.all(hot.status == d.abi.TRAJ_STOPPED)
+    o = oracle.run_solver(mk(), n_threads=8)
+    assert_same_counters(hot, o)
+    assert np.array_equal(hot.p, o.p) and np.array_equal(hot.aux, o.aux)
+    # FAST: pre-combined interpolant -> event times within tolerance, same event counts
+    f = mk("fast").run()
+    assert f.totals["kernel_kind"] == KERNEL_ODE_EVENT
+    assert np.array_equal(f.events, hot.events)
+    few = refl <= 10                      # the billiard map is chaotic: compare short itineraries
+    assert np.max(np.abs(f.p[few] - hot.p[few])) < 1e-9
+
+
+def _egg_with_reflections(n, refl, arith):
+    phi = 2.0 * np.pi * np.arange(n) / n
+    y0 = np.stack([np.zeros(n), np.full(n, 0.1), 0.5 * np.cos(phi), 0.5 * np.sin(phi)], axis=1)
+    return (d.Solver.new().initial(y0).equation(d.systems.EggBilliard, refl.reshape(-1, 1))
+            .interval(0.0, math.inf).stepsize(0.5).on_mut(d.Locator.above_zero("boundary"), "reflect")
+            .arith(arith).max_steps(100000))
+
+
+def test_event_kernel_fast_event_log_vs_oracle(oracle):
+    g = cases.bouncing_ball(n=64, t1=6.0, arith="fast").run()
+    assert g.totals["kernel_kind"] == KERNEL_ODE_EVENT
+    o = oracle.run_solver(cases.bouncing_ball(n=64, t1=6.0), n_threads=8)
+    assert np.array_equal(g.event_n, o.event_n) and np.array_equal(g.event_index, o.event_index)
+    assert np.max(np.abs(g.event_t - o.event_t)) < 1e-11     # "event times within the solver tolerance"
+    assert np.max(np.abs(g.p - o.p)) < 1e-10
+
+
+def test_event_kernel_step_limit_status(oracle):
+    # max_steps guard on an unbounded interval (the egg billiard never stops by itself with a huge quota)
+    mk = lambda: (_egg_with_reflections(40, np.full(40, 1e9), "strict").max_steps(500))
+    hot = mk().run()
+    assert hot.totals["kernel_kind"] == KERNEL_ODE_EVENT
+    o = oracle.run_solver(mk(), n_threads=4)
+    assert np.all(hot.status == 16) and np.array_equal(hot.status, o.status)
+    assert np.array_equal(hot.steps, o.steps) and np.all(hot.steps == 500)
+
 # ---------------------------------------------------------------- DDE / NDDE
 def test_dde_constant_history_strict_bit_exact(oracle):
     # x' = a x + b x(t - 1) with constant history: no transcendental call anywhere
@@ -447,7 +538,6 @@ def test_adaptive_lorenz_short(oracle):
 
 
 # ---------------------------------------------------------------- adaptive hot path (ode_adaptive_kernel)
-KERNEL_GENERAL, KERNEL_ODE_FIXED, KERNEL_DDE_FIXED, KERNEL_ODE_ADAPTIVE = 0, 1, 2, 3
 
 
 def check_adaptive_counters(g, S):
@@ -654,16 +744,6 @@ def test_lyapunov_lorenz_fast_vs_strict_ensemble_mean():
 
 # ---------------------------------------------------------------- fixed step + Periodic callbacks (ode_fixed_periodic_kernel)
 KERNEL_ODE_FIXED_PERIODIC = 4
-
-
-def run_general(make):
-    os.environ["DFB_FORCE_GENERAL"] = "1"
-    try:
-        r = make().run()
-    finally:
-        del os.environ["DFB_FORCE_GENERAL"]
-    assert r.totals["kernel_kind"] == KERNEL_GENERAL
-    return r
 
 
 @pytest.mark.parametrize("arith", ["strict", "fast"])

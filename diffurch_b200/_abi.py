@@ -28,6 +28,10 @@ TRAJ_STEP_LIMIT = 16
 TRAJ_RING_OVERFLOW = 32
 TRAJ_STOPPED = 64
 TRAJ_DISCO_OVERFLOW = 128
+TRAJ_STEPSIZE_FLOOR = 256
+# dfb_kernel_kind (dfb_totals.kernel_kind)
+KERNEL_GENERAL, KERNEL_ODE_FIXED, KERNEL_DDE_FIXED, KERNEL_ODE_ADAPTIVE = 0, 1, 2, 3
+KERNEL_ODE_FIXED_PERIODIC, KERNEL_ODE_EVENT = 4, 5
 
 # dfb_system_id
 SYS_LORENZ = 1
@@ -47,6 +51,7 @@ SYS_BOUNCING_BALL = 14
 SYS_EGG_BILLIARD = 15
 SYS_RELAY_MSIGN = 16
 SYS_DDE_RELAY_CLAMP = 17
+SYS_USER_BASE = 1000  # ids of systems registered with dfb_register_plugin start here
 
 # dfb_history_id
 HIST_CONSTANT, HIST_SIN, HIST_SIN_NODERIV, HIST_INV_SQUARE = 0, 1, 2, 3
@@ -154,7 +159,7 @@ class Totals(C.Structure):
 # Every symbol include/diffurch_b200.h declares (checked by tests/test_abi.py).
 EXPORTED_SYMBOLS = [
     "dfb_tableau_by_name", "dfb_tableau_generic_order_2", "dfb_tableau_generic_order_3",
-    "dfb_problem_default", "dfb_system_info_get",
+    "dfb_problem_default", "dfb_system_info_get", "dfb_register_plugin",
     "dfb_create", "dfb_destroy",
     "dfb_set_initial", "dfb_set_params", "dfb_set_initial_device", "dfb_set_params_device",
     "dfb_run", "dfb_synchronize",

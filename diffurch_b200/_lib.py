@@ -34,6 +34,7 @@ def _load():
                                                   C.POINTER(abi.Tableau)]),
         "dfb_problem_default": (C.c_int, [C.POINTER(abi.Problem)]),
         "dfb_system_info_get": (C.c_int, [C.c_int32, C.POINTER(abi.SystemInfo)]),
+        "dfb_register_plugin": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32)]),
         "dfb_create": (C.c_int, [C.POINTER(abi.Problem), C.c_size_t, C.c_int, C.POINTER(H)]),
         "dfb_destroy": (None, [H]),
         "dfb_set_initial": (C.c_int, [H, dp]),

@@ -21,49 +21,12 @@
 #include "host/tableaux.hpp"
 #include "launch.hpp"
 
-// OdeFixedArgs is declared per arithmetic namespace in dev/ode_fixed.cuh; the
-// two definitions are layout-identical.  Pull both in through small shims.
-namespace dfb_strict {
-int run_ode_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h,
-                       size_t n, const double* y0, const double* params, double* t_final,
-                       double* y_final, unsigned long long* steps, unsigned long long* rhs_evals,
-                       uint32_t* status, cudaStream_t stream);
-int run_ode_fixed_periodic_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h,
-                                size_t n, const double* y0, const double* params, double* t_final,
-                                double* y_final, double* aux_final, unsigned long long* steps,
-                                unsigned long long* events, unsigned long long* rhs_evals,
-                                uint32_t* status, int n_loc, const dfb_locator* loc, int event_capacity,
-                                double* ev_t, int32_t* ev_idx, uint32_t* n_events, cudaStream_t stream);
-int run_ode_event_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h, long long max_steps,
-                       size_t n, const double* y0, const double* params, double* t_final, double* y_final,
-                       double* aux_final, unsigned long long* steps, unsigned long long* events,
-                       unsigned long long* rhs_evals, uint32_t* status, int n_loc, const dfb_locator* loc,
-                       int event_capacity, double* ev_t, int32_t* ev_idx, uint32_t* n_events, int trace_every,
-                       int trace_capacity, double* trace_t, double* trace_y, uint32_t* n_samples,
-                       unsigned long long* queue, int locate_batch, int locate_wait, int n_sm,
-                       cudaStream_t stream);
-}
-namespace dfb_fast {
-int run_ode_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h,
-                       size_t n, const double* y0, const double* params, double* t_final,
-                       double* y_final, unsigned long long* steps, unsigned long long* rhs_evals,
-                       uint32_t* status, cudaStream_t stream);
-int run_ode_fixed_periodic_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h,
-                                size_t n, const double* y0, const double* params, double* t_final,
-                                double* y_final, double* aux_final, unsigned long long* steps,
-                                unsigned long long* events, unsigned long long* rhs_evals,
-                                uint32_t* status, int n_loc, const dfb_locator* loc, int event_capacity,
-                                double* ev_t, int32_t* ev_idx, uint32_t* n_events, cudaStream_t stream);
-int run_ode_event_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h, long long max_steps,
-                       size_t n, const double* y0, const double* params, double* t_final, double* y_final,
-                       double* aux_final, unsigned long long* steps, unsigned long long* events,
-                       unsigned long long* rhs_evals, uint32_t* status, int n_loc, const dfb_locator* loc,
-                       int event_capacity, double* ev_t, int32_t* ev_idx, uint32_t* n_events, int trace_every,
-                       int trace_capacity, double* trace_t, double* trace_y, uint32_t* n_samples,
-                       unsigned long long* queue, int locate_batch, int locate_wait, int n_sm,
-                       cudaStream_t stream);
-}
+#include "launch_table.hpp"
 
+// Launchers exported by the kernel translation units (argument blocks are declared per
+// arithmetic namespace in dev/*.cuh; the shims take plain arguments).
+DFB_DECLARE_SHIMS(dfb_strict)
+DFB_DECLARE_SHIMS(dfb_fast)
 namespace dfb_fast {
 int run_dde_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h,
                        double max_delay, int history_id, int ring_capacity, size_t n,
@@ -96,6 +59,39 @@ int fail(int code, const std::string& msg) {
 struct SysInfo {
   int id, n_state, n_params, n_aux, n_detectors, n_callbacks, uses_history;
 };
+
+// ---- launch tables: built-in systems, and user-system plugins (dfb_register_plugin) ----
+const DfbLaunchTable kBuiltinFast = {
+    dfb_fast::run_ode_fixed_shim, dfb_fast::run_ode_fixed_periodic_shim, dfb_fast::run_ode_event_shim,
+    dfb_fast::run_ode_adaptive_shim, dfb_fast::run_dde_fixed_shim,
+    {dfb_fast::launch_general_g1, dfb_fast::launch_general_g2, dfb_fast::launch_general_g3,
+     dfb_fast::launch_general_g4, dfb_fast::launch_general_g5}, 5};
+const DfbLaunchTable kBuiltinStrict = {
+    dfb_strict::run_ode_fixed_shim, dfb_strict::run_ode_fixed_periodic_shim, dfb_strict::run_ode_event_shim,
+    nullptr, nullptr,
+    {dfb_strict::launch_general_g1, dfb_strict::launch_general_g2, dfb_strict::launch_general_g3,
+     dfb_strict::launch_general_g4, dfb_strict::launch_general_g5}, 5};
+
+struct PluginSys {
+  SysInfo info;
+  bool dde_hot_ok;
+  std::string name, path;
+  void* dl;
+  DfbLaunchTable fast, strict;
+};
+std::vector<PluginSys*>& plugins() {
+  static std::vector<PluginSys*> v;  // never freed: tables must outlive every handle
+  return v;
+}
+const PluginSys* find_plugin(int id) {
+  const int i = id - DFB_SYS_USER_BASE;
+  if (i < 0 || size_t(i) >= plugins().size()) return nullptr;
+  return plugins()[size_t(i)];
+}
+const DfbLaunchTable& table_for(int system_id, int arith) {
+  if (const PluginSys* ps = find_plugin(system_id)) return arith == DFB_ARITH_FAST ? ps->fast : ps->strict;
+  return arith == DFB_ARITH_FAST ? kBuiltinFast : kBuiltinStrict;
+}
 const SysInfo kSystems[] = {
     {DFB_SYS_LORENZ, 3, 3, 0, 0, 0, 0},
     {DFB_SYS_LORENZ_VARIATIONAL, 12, 3, 3, 0, 1, 0},
@@ -118,7 +114,12 @@ const SysInfo kSystems[] = {
 const SysInfo* find_system(int id) {
   for (const SysInfo& s : kSystems)
     if (s.id == id) return &s;
+  if (const PluginSys* ps = find_plugin(id)) return &ps->info;
   return nullptr;
+}
+bool dde_hot_system(int id) {
+  if (const PluginSys* ps = find_plugin(id)) return ps->dde_hot_ok;
+  return id == DFB_SYS_DDE_LINEAR || id == DFB_SYS_NDDE_LINEAR;
 }
 
 // ---- layout kernels: caller-facing array-of-states <-> device structure-of-arrays
@@ -295,15 +296,10 @@ int launch_general(dfb_handle* h, const DevProblem& P, cudaStream_t stream) {
   cfg.locate_max_wait = h->locate_max_wait;
   const bool has_loc = P.n_loc > 0;
   const bool fast = h->prob.arith == DFB_ARITH_FAST;
-  typedef int (*Fn)(const DevProblem&, int, bool, const LaunchCfg&, int);
-  const Fn strict_fns[] = {dfb_strict::launch_general_g1, dfb_strict::launch_general_g2,
-                           dfb_strict::launch_general_g3, dfb_strict::launch_general_g4,
-                           dfb_strict::launch_general_g5};
-  const Fn fast_fns[] = {dfb_fast::launch_general_g1, dfb_fast::launch_general_g2,
-                         dfb_fast::launch_general_g3, dfb_fast::launch_general_g4,
-                         dfb_fast::launch_general_g5};
-  for (int g = 0; g < 5; ++g) {
-    const int rc = (fast ? fast_fns : strict_fns)[g](P, h->prob.system_id, has_loc, cfg, h->locate_batch);
+  const DfbLaunchTable& T = table_for(h->prob.system_id, fast ? DFB_ARITH_FAST : DFB_ARITH_STRICT);
+  for (int g = 0; g < T.n_general; ++g) {
+    if (!T.general[g]) continue;
+    const int rc = T.general[g](P, h->prob.system_id, has_loc, cfg, h->locate_batch);
     if (rc == -1) continue;
     if (rc != 0)
       return fail(DFB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(cudaError_t(rc)));
@@ -361,6 +357,45 @@ int dfb_system_info_get(int32_t system_id, dfb_system_info* out) {
   out->n_detectors = s->n_detectors;
   out->n_callbacks = s->n_callbacks;
   out->uses_history = s->uses_history;
+  return DFB_OK;
+}
+
+int dfb_register_plugin(const char* so_path, int32_t* system_id_out) {
+  if (!so_path || !system_id_out) return fail(DFB_ERR_INVALID, "null argument");
+  for (size_t i = 0; i < plugins().size(); ++i)
+    if (plugins()[i]->path == so_path) {  // idempotent per path
+      *system_id_out = DFB_SYS_USER_BASE + int32_t(i);
+      return DFB_OK;
+    }
+  void* dl = dlopen(so_path, RTLD_NOW | RTLD_LOCAL);
+  if (!dl) return fail(DFB_ERR_INVALID, std::string("dlopen: ") + dlerror());
+  DfbPluginDescribeFn describe = reinterpret_cast<DfbPluginDescribeFn>(dlsym(dl, "dfb_plugin_describe"));
+  if (!describe) {
+    dlclose(dl);
+    return fail(DFB_ERR_INVALID, "not a diffurch_b200 plugin: dfb_plugin_describe missing");
+  }
+  dfb_plugin_desc d;
+  std::memset(&d, 0, sizeof(d));
+  if (describe(&d) != 0 || d.plugin_abi != DFB_PLUGIN_ABI) {
+    dlclose(dl);
+    return fail(DFB_ERR_INVALID, "plugin ABI mismatch: rebuild it with diffurch_b200.user.build_user_system");
+  }
+  if (d.n_state < 1 || d.n_state > DFB_MAX_STATE || d.n_params < 0 || d.n_params > DFB_MAX_PARAMS ||
+      d.n_aux < 0 || d.n_aux > DFB_MAX_AUX) {
+    dlclose(dl);
+    return fail(DFB_ERR_INVALID, "plugin system exceeds DFB_MAX_STATE / DFB_MAX_PARAMS / DFB_MAX_AUX");
+  }
+  PluginSys* ps = new PluginSys();
+  const int id = DFB_SYS_USER_BASE + int(plugins().size());
+  ps->info = SysInfo{id, d.n_state, d.n_params, d.n_aux, d.n_detectors, d.n_callbacks, d.uses_history};
+  ps->dde_hot_ok = d.dde_hot_ok != 0;
+  ps->name = d.name ? d.name : "";
+  ps->path = so_path;
+  ps->dl = dl;
+  ps->fast = d.fast;
+  ps->strict = d.strict;
+  plugins().push_back(ps);
+  *system_id_out = id;
   return DFB_OK;
 }
 
@@ -437,7 +472,7 @@ int dfb_create(const dfb_problem* desc, size_t n_traj, int device, dfb_handle** 
     h->dde_hot = info->uses_history && desc->arith == DFB_ARITH_FAST &&
                  desc->stepsize_kind == DFB_STEP_FIXED && desc->n_loc == 0 && desc->n_disco == 0 &&
                  desc->trace_every == 0 && desc->max_steps == 0 && shape_ok &&
-                 (desc->system_id == DFB_SYS_DDE_LINEAR || desc->system_id == DFB_SYS_NDDE_LINEAR) &&
+                 dde_hot_system(desc->system_id) && table_for(desc->system_id, DFB_ARITH_FAST).dde_fixed &&
                  std::isfinite(desc->max_delay) && desc->max_delay > 0.0 &&
                  desc->max_delay / desc->h < 60000.0 && !std::getenv("DFB_FORCE_GENERAL");
     if (h->dde_hot) {  // the kernel indexes the ring with 32-bit offsets and counts steps in an int
@@ -549,6 +584,7 @@ int dfb_run(dfb_handle* h, void* stream_v) {
   const double* y0 = h->d_y0_ext ? h->d_y0_ext : h->d_y0;
   const double* params = h->d_params_ext ? h->d_params_ext : h->d_params;
   h->launches = 0;
+  const DfbLaunchTable& T = table_for(p.system_id, p.arith);
 
   // Hot path: fixed step, no locators, no history, final state only.
   const bool hot_eligible = p.stepsize_kind == DFB_STEP_FIXED && p.n_loc == 0 &&
@@ -561,8 +597,8 @@ int dfb_run(dfb_handle* h, void* stream_v) {
     DFB_CUDA(cudaMemsetAsync(h->d_events, 0, n * sizeof(unsigned long long), stream));
     if (h->info.n_aux) DFB_CUDA(cudaMemsetAsync(h->d_aux, 0, n * h->info.n_aux * sizeof(double), stream));
     DFB_CUDA(cudaEventRecord(h->ev0, stream));
-    auto shim = p.arith == DFB_ARITH_FAST ? dfb_fast::run_ode_fixed_shim : dfb_strict::run_ode_fixed_shim;
-    const int rc = shim(p.system_id, p.rk, p.t0, p.t1, p.h, n, y0, params, h->d_t, h->d_y,
+    const DfbOdeFixedFn shim = T.ode_fixed;
+    const int rc = !shim ? -1 : shim(p.system_id, p.rk, p.t0, p.t1, p.h, n, y0, params, h->d_t, h->d_y,
                         h->d_steps, h->d_rhs, h->d_status, stream);
     if (rc > 0) return fail(DFB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(cudaError_t(rc)));
     if (rc == 0) {
@@ -586,9 +622,8 @@ int dfb_run(dfb_handle* h, void* stream_v) {
   if (periodic_eligible) {
     DFB_CUDA(cudaMemsetAsync(h->d_rejected, 0, n * sizeof(unsigned long long), stream));
     DFB_CUDA(cudaEventRecord(h->ev0, stream));
-    auto shim = p.arith == DFB_ARITH_FAST ? dfb_fast::run_ode_fixed_periodic_shim
-                                          : dfb_strict::run_ode_fixed_periodic_shim;
-    const int rc = shim(p.system_id, p.rk, p.t0, p.t1, p.h, n, y0, params, h->d_t, h->d_y,
+    const DfbOdePeriodicFn shim = T.ode_periodic;
+    const int rc = !shim ? -1 : shim(p.system_id, p.rk, p.t0, p.t1, p.h, n, y0, params, h->d_t, h->d_y,
                         h->info.n_aux ? h->d_aux : nullptr, h->d_steps, h->d_events, h->d_rhs, h->d_status,
                         p.n_loc, p.loc, p.event_capacity, h->d_ev_t, h->d_ev_idx, h->d_nevents, stream);
     if (rc > 0) return fail(DFB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(cudaError_t(rc)));
@@ -611,9 +646,9 @@ int dfb_run(dfb_handle* h, void* stream_v) {
     DFB_CUDA(cudaMemsetAsync(h->d_rejected, 0, n * sizeof(unsigned long long), stream));
     DFB_CUDA(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned long long), stream));
     DFB_CUDA(cudaEventRecord(h->ev0, stream));
-    auto shim = p.arith == DFB_ARITH_FAST ? dfb_fast::run_ode_event_shim : dfb_strict::run_ode_event_shim;
+    const DfbOdeEventFn shim = T.ode_event;
     const bool tracing = h->d_trace_t && p.trace_every > 0;
-    const int rc = shim(p.system_id, p.rk, p.t0, p.t1, p.h, p.max_steps, n, y0, params, h->d_t, h->d_y,
+    const int rc = !shim ? -1 : shim(p.system_id, p.rk, p.t0, p.t1, p.h, p.max_steps, n, y0, params, h->d_t, h->d_y,
                         h->info.n_aux ? h->d_aux : nullptr, h->d_steps, h->d_events, h->d_rhs, h->d_status,
                         p.n_loc, p.loc, p.event_capacity, h->d_ev_t, h->d_ev_idx, h->d_nevents,
                         tracing ? p.trace_every : 0, p.trace_capacity, tracing ? h->d_trace_t : nullptr,
@@ -641,7 +676,7 @@ int dfb_run(dfb_handle* h, void* stream_v) {
     if (h->info.n_aux) DFB_CUDA(cudaMemsetAsync(h->d_aux, 0, n * h->info.n_aux * sizeof(double), stream));
     DFB_CUDA(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned long long), stream));
     DFB_CUDA(cudaEventRecord(h->ev0, stream));
-    const int rc = dfb_fast::run_ode_adaptive_shim(p.system_id, p.rk, p.automatic, p.t0, p.t1, n, y0, params,
+    const int rc = !T.ode_adaptive ? -1 : T.ode_adaptive(p.system_id, p.rk, p.automatic, p.t0, p.t1, n, y0, params,
                                                    h->d_t, h->d_y, h->d_steps, h->d_rejected, h->d_rhs,
                                                    h->d_status, h->d_queue, h->n_sm, stream);
     if (rc > 0) return fail(DFB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(cudaError_t(rc)));
@@ -659,7 +694,7 @@ int dfb_run(dfb_handle* h, void* stream_v) {
     DFB_CUDA(cudaMemsetAsync(h->d_rejected, 0, n * sizeof(unsigned long long), stream));
     DFB_CUDA(cudaMemsetAsync(h->d_events, 0, n * sizeof(unsigned long long), stream));
     DFB_CUDA(cudaEventRecord(h->ev0, stream));
-    const int rc = dfb_fast::run_dde_fixed_shim(p.system_id, p.rk, p.t0, p.t1, p.h, p.max_delay,
+    const int rc = !T.dde_fixed ? -1 : T.dde_fixed(p.system_id, p.rk, p.t0, p.t1, p.h, p.max_delay,
                                                 p.history_id, h->ring_capacity, n, y0, params,
                                                 h->d_ring_coeff, h->d_t, h->d_y, h->d_steps, h->d_rhs,
                                                 h->d_status, stream);

@@ -136,6 +136,9 @@ struct SysBase {
   static constexpr bool pure_rhs = true;
   // no functor of the system (rhs, detectors, callbacks) reads the view's `d` (state_fn.rs:17)
   static constexpr bool reads_d = false;
+  // the system has exactly one constant delay and says so with `const_delay(prm)`: lets the
+  // coefficient-ring DDE kernel (dev/dde_fixed.cuh) take it
+  static constexpr bool has_const_delay = false;
   template <class V>
   __device__ static double detector(int, const V&, const double*) { return 0.0; }
   template <class M>
@@ -282,6 +285,7 @@ struct SysDdeLinear : SysBase {  // tests/equation_types.rs:131
   static constexpr bool uses_history = true;
   static constexpr bool pure_rhs = false;
   // the one constant delay of this equation (lets the streaming-window kernel take it)
+  static constexpr bool has_const_delay = true;
   __device__ __forceinline__ static double const_delay(const double* prm) { return prm[2]; }
   template <class V>
   __device__ __forceinline__ static void rhs(const V& s, const double* prm, double* out) {
@@ -295,6 +299,7 @@ struct SysNddeLinear : SysBase {  // tests/equation_types.rs:150
   static constexpr int ID = DFB_SYS_NDDE_LINEAR, N = 1, NP = 4;
   static constexpr bool uses_history = true;
   static constexpr bool pure_rhs = false;
+  static constexpr bool has_const_delay = true;
   __device__ __forceinline__ static double const_delay(const double* prm) { return prm[2]; }
   template <class V>
   __device__ __forceinline__ static void rhs(const V& s, const double* prm, double* out) {
@@ -390,3 +395,10 @@ struct SysDdeRelayClamp : SysBase {  // examples/dde-relay-clamp.rs:24-35
 };
 
 }  // namespace DFB_NS
+
+// A user-system plugin build (diffurch_b200.user.build_user_system) compiles the kernel
+// translation units with -DDFB_PLUGIN_HEADER="<user header>" -DDFB_PLUGIN_SYSTEM=<struct>: the
+// header is pulled in here, after the views and SysBase it builds on.
+#ifdef DFB_PLUGIN_HEADER
+#include DFB_PLUGIN_HEADER
+#endif

@@ -116,12 +116,19 @@ int run_dde_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t
   A.ring = ring;
   int rc = 0;
   bool ok = false;
+#ifdef DFB_PLUGIN_SYSTEM
+  (void)system_id;
+  if constexpr (DFB_PLUGIN_SYSTEM::uses_history && DFB_PLUGIN_SYSTEM::has_const_delay)
+    ok = launch_sys<DFB_PLUGIN_SYSTEM>(rk.S, rk.I, am, bm, bim, A, stream, &rc);
+  return ok ? rc : -1;
+#else
   switch (system_id) {
     case DFB_SYS_DDE_LINEAR: ok = launch_sys<SysDdeLinear>(rk.S, rk.I, am, bm, bim, A, stream, &rc); break;
     case DFB_SYS_NDDE_LINEAR: ok = launch_sys<SysNddeLinear>(rk.S, rk.I, am, bm, bim, A, stream, &rc); break;
     default: break;
   }
   return ok ? rc : -1;
+#endif
 }
 
 }  // namespace DFB_NS

@@ -33,6 +33,11 @@ int launch_one(const DevProblem& P, bool has_loc, const LaunchCfg& c, int thr) {
 int DFB_CAT(launch_general_g, DFB_GROUP)(const DevProblem& P, int system_id, bool has_loc,
                                          const LaunchCfg& c, int thr) {
   const int S = P.rk.S, I = P.rk.I;
+#ifdef DFB_PLUGIN_SYSTEM
+  (void)system_id;
+  SHAPE(DFB_PLUGIN_SYSTEM, 7, 5) SHAPE(DFB_PLUGIN_SYSTEM, 5, 4) SHAPE(DFB_PLUGIN_SYSTEM, 4, 2)
+  return -1;
+#else
   switch (system_id) {
 #if DFB_GROUP == 1
     case DFB_SYS_LORENZ: ALL_SHAPES(SysLorenz) break;
@@ -63,6 +68,7 @@ int DFB_CAT(launch_general_g, DFB_GROUP)(const DevProblem& P, int system_id, boo
   (void)S;
   (void)I;
   return -1;
+#endif
 }
 
 }  // namespace DFB_NS

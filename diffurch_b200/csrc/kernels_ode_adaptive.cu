@@ -108,6 +108,12 @@ int run_ode_adaptive_shim(int system_id, const dfb_tableau& rk, const dfb_auto_s
   A.queue = queue;
   int rc = 0;
   bool ok = false;
+#ifdef DFB_PLUGIN_SYSTEM
+  (void)system_id;
+  if constexpr (!DFB_PLUGIN_SYSTEM::uses_history && DFB_PLUGIN_SYSTEM::pure_rhs)
+    ok = launch_common<DFB_PLUGIN_SYSTEM>(rk.S, am, bm, em, A, n_sm, stream, &rc);
+  return ok ? rc : -1;
+#else
   switch (system_id) {
     case DFB_SYS_LORENZ: ok = launch_all_shapes<SysLorenz>(rk.S, am, bm, em, A, n_sm, stream, &rc); break;
     case DFB_SYS_HARMONIC: ok = launch_all_shapes<SysHarmonic>(rk.S, am, bm, em, A, n_sm, stream, &rc); break;
@@ -121,6 +127,7 @@ int run_ode_adaptive_shim(int system_id, const dfb_tableau& rk, const dfb_auto_s
     default: break;
   }
   return ok ? rc : -1;
+#endif
 }
 
 }  // namespace DFB_NS

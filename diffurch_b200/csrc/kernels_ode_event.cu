@@ -38,6 +38,14 @@ bool try_launch(int S_rt, int I_rt, const OdeFixedArgs& A, int n_sm, cudaStream_
 int launch_ode_event(int system_id, int S, int I, const OdeFixedArgs& A, int n_sm, cudaStream_t stream) {
   int rc = 0;
   bool ok = false;
+#ifdef DFB_PLUGIN_SYSTEM
+  (void)system_id;
+  if constexpr (!DFB_PLUGIN_SYSTEM::uses_history && !DFB_PLUGIN_SYSTEM::reads_d)
+    ok = try_launch<DFB_PLUGIN_SYSTEM, 7, 5>(S, I, A, n_sm, stream, &rc) ||
+         try_launch<DFB_PLUGIN_SYSTEM, 5, 4>(S, I, A, n_sm, stream, &rc) ||
+         try_launch<DFB_PLUGIN_SYSTEM, 4, 2>(S, I, A, n_sm, stream, &rc);
+  return ok ? rc : -1;
+#else
   switch (system_id) {
     case DFB_SYS_BOUNCING_BALL:
       ok = try_launch<SysBouncingBall, 7, 5>(S, I, A, n_sm, stream, &rc) ||
@@ -54,6 +62,7 @@ int launch_ode_event(int system_id, int S, int I, const OdeFixedArgs& A, int n_s
     default: break;
   }
   return ok ? rc : -1;
+#endif
 }
 
 int run_ode_event_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h, long long max_steps,

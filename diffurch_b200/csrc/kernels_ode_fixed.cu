@@ -82,6 +82,12 @@ int launch_ode_fixed_periodic(int system_id, int S, unsigned long long amask, un
                               const OdeFixedArgs& A, cudaStream_t stream) {
   int rc = 0;
   bool ok = false;
+#ifdef DFB_PLUGIN_SYSTEM
+  (void)system_id;
+  if constexpr (!DFB_PLUGIN_SYSTEM::uses_history && !DFB_PLUGIN_SYSTEM::reads_d)
+    ok = launch_periodic_common<DFB_PLUGIN_SYSTEM>(S, amask, bmask, A, stream, &rc);
+  return ok ? rc : -1;
+#else
   switch (system_id) {
     case DFB_SYS_LORENZ_VARIATIONAL:
       ok = launch_periodic_common<SysLorenzVariational>(S, amask, bmask, A, stream, &rc);
@@ -99,6 +105,7 @@ int launch_ode_fixed_periodic(int system_id, int S, unsigned long long amask, un
     default: break;
   }
   return ok ? rc : -1;
+#endif
 }
 
 // returns 0 = launched, >0 = CUDA error code, -1 = no compiled kernel for this combination
@@ -106,6 +113,12 @@ int launch_ode_fixed(int system_id, int S, unsigned long long amask, unsigned bm
                      const OdeFixedArgs& A, cudaStream_t stream) {
   int rc = 0;
   bool ok = false;
+#ifdef DFB_PLUGIN_SYSTEM
+  (void)system_id;
+  if constexpr (!DFB_PLUGIN_SYSTEM::uses_history && !DFB_PLUGIN_SYSTEM::reads_d)
+    ok = launch_common<DFB_PLUGIN_SYSTEM>(S, amask, bmask, A, stream, &rc);
+  return ok ? rc : -1;
+#else
   switch (system_id) {
     case DFB_SYS_LORENZ: ok = launch_all_shapes<SysLorenz>(S, amask, bmask, A, stream, &rc); break;
     case DFB_SYS_LINEAR1: ok = launch_all_shapes<SysLinear1>(S, amask, bmask, A, stream, &rc); break;
@@ -121,6 +134,7 @@ int launch_ode_fixed(int system_id, int S, unsigned long long amask, unsigned bm
     default: break;
   }
   return ok ? rc : -1;
+#endif
 }
 
 // Host shim used by api.cu: builds the argument block (pre-scaled rows are

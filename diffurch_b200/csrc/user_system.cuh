@@ -1,0 +1,21 @@
+// What a user-system header includes.  Example (tests/plugins/van_der_pol.cuh):
+//
+//   #include "user_system.cuh"
+//   namespace DFB_NS {
+//   struct SysVanDerPol : SysBase {          // x'' - mu (1 - x^2) x' + x = 0
+//     static constexpr int N = 2, NP = 1;    // state size, parameters per trajectory
+//     template <class V>                     // V = StateRef: {t, p, d, t_prev, p_prev, p_at(), d_at()}
+//     __device__ __forceinline__ static void rhs(const V& s, const double* prm, double* out) {
+//       out[0] = s.p[1];
+//       out[1] = prm[0] * (1.0 - s.p[0] * s.p[0]) * s.p[1] - s.p[0];
+//     }
+//   };
+//   }  // namespace DFB_NS
+//
+// Optional members (defaults in SysBase): NA (aux accumulators), ND / NC (detector / callback
+// counts), `detector(id, view, prm)`, `callback(id, mut_view, prm, aux)`, `uses_history` +
+// `has_const_delay` + `const_delay(prm)` for delay equations, `pure_rhs = false` if rhs reads
+// p_prev / t_prev / d / the history.  The header is compiled twice, into namespaces dfb_strict
+// (-fmad=false) and dfb_fast; DFB_NS names the current one.
+#pragma once
+#include "dev/systems.cuh"

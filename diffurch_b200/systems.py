@@ -68,3 +68,9 @@ ALL = [Lorenz, LorenzVariational, Linear1, Linear1Sin, Linear3, Linear3Matrix, H
        PowerDecay, Constant3, Time3, Zero1, DdeLinear, NddeLinear, BouncingBall, EggBilliard,
        RelayMsign, DdeRelayClamp]
 BY_ID = {s.id: s for s in ALL}
+
+
+def register(system):
+    """Add a user system (diffurch_b200.user.load_user_system) to the id registry."""
+    BY_ID[system.id] = system
+    return system

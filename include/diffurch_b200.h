@@ -151,7 +151,9 @@ typedef enum dfb_system_id {
   DFB_SYS_RELAY_MSIGN = 16,
   /* examples/dde-relay-clamp.rs:24-35. N=2, params {alpha, sigma, T};
    * detector 1 = |x(t-T)| - 1 */
-  DFB_SYS_DDE_RELAY_CLAMP = 17
+  DFB_SYS_DDE_RELAY_CLAMP = 17,
+  /* ids >= DFB_SYS_USER_BASE are user systems registered with dfb_register_plugin */
+  DFB_SYS_USER_BASE = 1000
 } dfb_system_id;
 
 /* `Solver::initial` argument kinds (initial_condition.rs:15-50). */
@@ -281,6 +283,15 @@ typedef struct dfb_system_info {
   int32_t n_state, n_params, n_aux, n_detectors, n_callbacks, uses_history;
 } dfb_system_info;
 DFB_API int dfb_system_info_get(int32_t system_id, dfb_system_info* out);
+
+/* User-defined systems.  `Solver::equation` (solver.rs:135) takes ANY closure; a closure cannot
+ * cross this ABI, so its CUDA restatement — a struct with the functor signatures of
+ * diffurch_b200/csrc/dev/systems.cuh (rhs / detector / callback over StateRef / StateRefMut,
+ * reference state_fn.rs:13-98) — is compiled against the same kernel templates into a plugin
+ * shared object (python: diffurch_b200.user.build_user_system; or nvcc by hand)
+ * and registered here.  Returns the system id to put into dfb_problem.system_id.  Registering
+ * the same path twice returns the same id.  Plugins stay loaded for the life of the process. */
+DFB_API int dfb_register_plugin(const char* so_path, int32_t* system_id_out);
 
 /* ------------------------------------------------------------------ handle */
 typedef struct dfb_handle dfb_handle;

@@ -6,7 +6,7 @@ compiled library reports.
 """
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_STAGES = 7
 MAX_INTERP = 5
 MAX_STATE = 12
@@ -68,7 +68,8 @@ LOC_STATEFN, LOC_PERIODIC, LOC_PROPAGATION = 0, 1, 2
  LOCATE_BISECTION_BOOL, LOCATE_REGULA_FALSI) = range(7)
 
 # dfb_filter
-FILTER_NONE, FILTER_EVERY, FILTER_SEPARATED_BY, FILTER_IN_INTERVAL = 0, 1, 2, 3
+FILTER_NONE, FILTER_EVERY, FILTER_SEPARATED_BY, FILTER_IN_INTERVAL, FILTER_ON_TIMES = 0, 1, 2, 3, 4
+MAX_FILTER_TIMES = 8
 
 CB_NONE = 0
 
@@ -97,6 +98,7 @@ class Locator(C.Structure):
         ("_pad", C.c_int32),
         ("period", C.c_double), ("offset", C.c_double), ("delay", C.c_double),
         ("filter_a", C.c_double), ("filter_b", C.c_double),
+        ("filter_times", C.c_int32 * MAX_FILTER_TIMES),
     ]
 
 

@@ -507,6 +507,16 @@ struct Integrator {
         }
         return false;
       case DFB_FILTER_IN_INTERVAL: return t >= L.filter_a && t < L.filter_b;
+      case DFB_FILTER_ON_TIMES: {  // loc.rs:665-688: every_i counts detections, sep_prev walks the list
+        const int i = every_i[l];
+        const int pos = int(sep_prev[l]);
+        every_i[l] = i + 1;
+        if (pos < L.filter_n && i == L.filter_times[pos]) {
+          sep_prev[l] = double(pos + 1);
+          return true;
+        }
+        return false;
+      }
     }
     return true;
   }
@@ -522,7 +532,7 @@ struct Integrator {
       // LocCallback then calls locate() AGAIN (loc.rs:31-33, 733-746).
       return filter_pass(l, locate_base(l));
     }
-    if (L.filter == DFB_FILTER_EVERY) return filter_pass(l, t_curr);
+    if (L.filter == DFB_FILTER_EVERY || L.filter == DFB_FILTER_ON_TIMES) return filter_pass(l, t_curr);
     return true;
   }
 
@@ -591,8 +601,9 @@ struct Integrator {
     has_last_call = 0u;
     for (int l = 0; l < MAXL; ++l) {
       last_call[l] = 0.0;
-      every_i[l] = l < P.n_loc ? P.loc[l].filter_n - 1 : 0;
-      sep_prev[l] = -1.7976931348623157e308;  // T::min_value()
+      const bool on_times = l < P.n_loc && P.loc[l].filter == DFB_FILTER_ON_TIMES;
+      every_i[l] = on_times ? 0 : (l < P.n_loc ? P.loc[l].filter_n - 1 : 0);
+      sep_prev[l] = on_times ? 0.0 : -1.7976931348623157e308;  // T::min_value() / list position
       trk_t[l] = -1.7976931348623157e308;
       trk_order[l] = 0x7fffffffffffffffLL;    // usize::MAX
       trk_index[l] = 0;

@@ -213,6 +213,17 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
         }
         return false;
       case DFB_FILTER_IN_INTERVAL: return t >= L.filter_a && t < L.filter_b;
+      case DFB_FILTER_ON_TIMES: {  // loc.rs:665-688: every_i counts detections, sep_prev walks the list
+        const int i = every_i[l];
+        const int pos = int(sep_prev[l]);
+        every_i[l] = i + 1;
+        bool hit = false;
+#pragma unroll
+        for (int q = 0; q < DFB_MAX_FILTER_TIMES; ++q)  // unrolled: no run-time indexed array
+          if (q == pos && q < L.filter_n && i == L.filter_times[q]) hit = true;
+        if (hit) sep_prev[l] = double(pos + 1);
+        return hit;
+      }
     }
     return true;
   }
@@ -225,7 +236,7 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
       precombine();  // FilterLocated::detect locates at once (rare: filtered locators only)
       return filter_pass(L, l, locate_base(L));
     }
-    if (L.filter == DFB_FILTER_EVERY) return filter_pass(L, l, t_curr);
+    if (L.filter == DFB_FILTER_EVERY || L.filter == DFB_FILTER_ON_TIMES) return filter_pass(L, l, t_curr);
     return true;
   }
 
@@ -276,8 +287,9 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
 #pragma unroll
     for (int l = 0; l < NLOC; ++l) {
       last_call[l] = 0.0;
-      every_i[l] = l < A.n_loc ? A.loc[l].filter_n - 1 : 0;
-      sep_prev[l] = -1.7976931348623157e308;  // T::min_value()
+      const bool on_times = l < A.n_loc && A.loc[l].filter == DFB_FILTER_ON_TIMES;
+      every_i[l] = on_times ? 0 : (l < A.n_loc ? A.loc[l].filter_n - 1 : 0);
+      sep_prev[l] = on_times ? 0.0 : -1.7976931348623157e308;  // T::min_value() / list position
     }
     n_steps = n_events = n_evlog = n_samples = 0u;
     n_rhs = on_step_calls = 0ull;

@@ -69,6 +69,14 @@ struct Loc {
   Loc& every(int n) { l.filter = DFB_FILTER_EVERY, l.filter_n = n; return *this; }
   Loc& separated_by(double diff) { l.filter = DFB_FILTER_SEPARATED_BY, l.filter_a = diff; return *this; }
   Loc& in_interval(double a, double b) { l.filter = DFB_FILTER_IN_INTERVAL, l.filter_a = a, l.filter_b = b; return *this; }
+  // Filter::on_times (loc.rs:665-688): strictly increasing 0-based detection indices, at most DFB_MAX_FILTER_TIMES
+  Loc& on_times(std::initializer_list<int> idx) {
+    l.filter = DFB_FILTER_ON_TIMES;
+    l.filter_n = 0;
+    for (int i : idx)
+      if (l.filter_n < DFB_MAX_FILTER_TIMES) l.filter_times[l.filter_n++] = i;
+    return *this;
+  }
 };
 struct Locator {
   static Loc mk(int detector, int detection, int location) {

@@ -26,6 +26,7 @@ class _Loc:
         self.filter_n = 0
         self.filter_a = 0.0
         self.filter_b = 0.0
+        self.filter_times = ()
 
     # ---- Filter trait (loc.rs:603-689) ----
     def _with_filter(self, kind, n=0, a=0.0, b=0.0):
@@ -43,6 +44,17 @@ class _Loc:
 
     def in_interval(self, start, end):
         return self._with_filter(abi.FILTER_IN_INTERVAL, a=start, b=end)
+
+    def on_times(self, indices):
+        """``Filter::on_times(iter)`` (loc.rs:665-688): pass the detections whose 0-based index is
+        in `indices`.  The reference takes any iterator and walks it monotonically; the device path
+        takes a finite, strictly increasing list of at most ``MAX_FILTER_TIMES`` indices."""
+        idx = [int(i) for i in indices]
+        if len(idx) > abi.MAX_FILTER_TIMES or any(b <= a for a, b in zip(idx, idx[1:])) or any(i < 0 for i in idx):
+            raise ValueError(f"on_times takes <= {abi.MAX_FILTER_TIMES} strictly increasing indices")
+        r = self._with_filter(abi.FILTER_ON_TIMES, n=len(idx))
+        r.filter_times = tuple(idx)
+        return r
 
     # location-method overrides (the reference builds these by hand from LocatorStateFn)
     def with_location(self, location):
@@ -71,6 +83,8 @@ class _Loc:
         L.delay = float(self.delay)
         L.filter_a = self.filter_a
         L.filter_b = self.filter_b
+        for i in range(abi.MAX_FILTER_TIMES):
+            L.filter_times[i] = self.filter_times[i] if i < len(self.filter_times) else 0
 
 
 class Locator:

@@ -48,6 +48,7 @@ def build_user_system(header, struct_name, out_dir=None, force=False, verbose=Fa
     obj_dir = os.path.join(out_dir, f"{struct_name}_{tag}_obj")
     so = os.path.join(out_dir, f"libdfb_user_{struct_name}_{tag}.so")
     newest_dep = max(os.path.getmtime(os.path.join(r, f)) for r, _, fs in os.walk(CSRC) for f in fs)
+    newest_dep = max(newest_dep, os.path.getmtime(os.path.join(CSRC, "..", "..", "include", "diffurch_b200.h")))
     if not force and os.path.exists(so) and os.path.getmtime(so) >= max(newest_dep, os.path.getmtime(header)):
         return so
     os.makedirs(obj_dir, exist_ok=True)

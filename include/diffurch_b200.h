@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define DFB_ABI_VERSION 1
+#define DFB_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DFB_API __attribute__((visibility("default")))
@@ -191,8 +191,9 @@ typedef enum dfb_location {
  * index list stored in filter_times. */
 typedef enum dfb_filter {
   DFB_FILTER_NONE = 0, DFB_FILTER_EVERY = 1, DFB_FILTER_SEPARATED_BY = 2,
-  DFB_FILTER_IN_INTERVAL = 3
+  DFB_FILTER_IN_INTERVAL = 3, DFB_FILTER_ON_TIMES = 4
 } dfb_filter;
+#define DFB_MAX_FILTER_TIMES 8 /* on_times: a finite index list (the reference takes any iterator) */
 
 #define DFB_CB_NONE 0 /* `|_| {}` */
 
@@ -214,6 +215,8 @@ typedef struct dfb_locator {
   double delay;            /* PROPAGATION with detector_id == 0 */
   double filter_a;         /* separated_by(diff) / in_interval start (inclusive) */
   double filter_b;         /* in_interval end (exclusive) */
+  int32_t filter_times[DFB_MAX_FILTER_TIMES]; /* on_times (loc.rs:665-688): pass the detections whose
+                              0-based index is in this strictly increasing list of filter_n entries */
 } dfb_locator;
 
 /* ---------------------------------------------------------------- stepsize */

@@ -156,6 +156,22 @@ std::unique_ptr<LocBase<N, S, I>> make_locator(const dfb_locator& L, const doubl
     const double lo = L.filter_a, hi = L.filter_b;
     f->filter = [lo, hi](const Ref& s) { return s.t >= lo && s.t < hi; };  // `lo..hi`
     base = std::move(f);
+  } else if (L.filter == DFB_FILTER_ON_TIMES) {  // loc.rs:665-688
+    auto f = std::make_unique<FilterAfterDetection<N, S, I>>();
+    f->loc = std::move(base);
+    std::vector<size_t> times(L.filter_times, L.filter_times + L.filter_n);
+    auto i = std::make_shared<size_t>(0);
+    auto next = std::make_shared<size_t>(0);  // the Peekable iterator's position
+    f->filter = [times, i, next](const Ref&) {
+      if (*next < times.size() && *i == times[*next]) {
+        *next += 1;
+        *i += 1;
+        return true;
+      }
+      *i += 1;
+      return false;
+    };
+    base = std::move(f);
   }
   return base;
 }

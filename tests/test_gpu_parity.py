@@ -260,7 +260,8 @@ def test_all_detection_and_location_methods(oracle, detection, location):
 
 
 def test_filters_every_separated_in_interval(oracle):
-    for flt in (lambda L: L.every(3), lambda L: L.separated_by(2.5), lambda L: L.in_interval(2.0, 5.0)):
+    for flt in (lambda L: L.every(3), lambda L: L.separated_by(2.5), lambda L: L.in_interval(2.0, 5.0),
+                lambda L: L.on_times([0, 2, 3, 7])):
         def mk():
             return (d.Solver.new().initial([0.25, 0.0]).equation(d.systems.RelayMsign)
                     .interval(0.5, 10.5).stepsize(0.09).log_events(d.EventLog(64))

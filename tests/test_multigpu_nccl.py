@@ -85,3 +85,53 @@ def test_two_gpu_sharded_run_and_nccl_gather(tmp_path):
            .interval(0.0, 2.0).stepsize(1.0 / 250.0).run())
     assert np.array_equal(got["p"], one.p) and np.array_equal(got["t"], one.t)
     assert np.array_equal(got["y_all"], one.p) and np.array_equal(got["t_all"], one.t)
+
+
+def _lyap_worker(rank, world, port, n, tmax, out_path):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import cases
+    import diffurch_b200 as d
+    from diffurch_b200 import distributed as dd
+
+    rho = np.linspace(20.0, 40.0, n)
+    lo, hi = dd.shard_bounds(n, rank, world)
+    ens = cases.lyap_lorenz(tmax, rho=rho[lo:hi], arith="strict")
+    ens._device = rank
+    ens = ens.build()
+    ens.run()
+    comm = dd.NcclComm(rank, world)
+    m = hi - lo
+    t_all, y_all, aux_all = np.empty(m * world), np.empty((m * world, 12)), np.empty((m * world, 3))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    rc = d.lib.dfb_gather_final(ens._h, comm.handle, world, dp(t_all), dp(y_all), dp(aux_all))
+    assert rc == 0, d.lib.dfb_last_error()
+    if rank == 0:
+        np.savez(out_path, spectra=aux_all / tmax, y_all=y_all)
+    dist.barrier()
+    comm.destroy()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_two_gpu_lyapunov_spectra_gather(tmp_path):
+    # BASELINE configs[4]: Lyapunov batch over a parameter grid, spectra gathered over NCCL
+    import torch.multiprocessing as mp
+    import cases
+    n, tmax = 256, 20.0
+    out = str(tmp_path / "l.npz")
+    mp.spawn(_lyap_worker, args=(2, _free_port(), n, tmax, out), nprocs=2, join=True)
+    got = np.load(out)
+    one = cases.lyap_lorenz(tmax, rho=np.linspace(20.0, 40.0, n), arith="strict").run()
+    assert one.totals["kernel_kind"] == 4
+    assert np.array_equal(got["spectra"], one.aux / tmax)       # same kernel, same members: bit-identical
+    assert np.array_equal(got["y_all"], one.p)
+    # the three exponents sum to the trace of the Jacobian, -(sigma + 1 + beta)
+    assert np.max(np.abs(got["spectra"].sum(axis=1) + (10.0 + 1.0 + 8.0 / 3.0))) < 1e-6

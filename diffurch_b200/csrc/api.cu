@@ -266,9 +266,16 @@ int validate(const dfb_problem& p, const SysInfo** info_out) {
       return fail(DFB_ERR_INVALID, "Periodic period must be > 0");
     if (L.callback_id < 0 || L.callback_id > info->n_callbacks)
       return fail(DFB_ERR_INVALID, "callback_id not registered for this system");
-    if (L.filter < DFB_FILTER_NONE || L.filter > DFB_FILTER_IN_INTERVAL)
+    if (L.filter < DFB_FILTER_NONE || L.filter > DFB_FILTER_ON_TIMES)
       return fail(DFB_ERR_INVALID, "locator filter");
     if (L.filter == DFB_FILTER_EVERY && L.filter_n < 1) return fail(DFB_ERR_INVALID, "every(n): n >= 1");
+    if (L.filter == DFB_FILTER_ON_TIMES) {
+      if (L.filter_n < 0 || L.filter_n > DFB_MAX_FILTER_TIMES)
+        return fail(DFB_ERR_INVALID, "on_times: at most DFB_MAX_FILTER_TIMES indices");
+      for (int q = 0; q < L.filter_n; ++q)
+        if (L.filter_times[q] < 0 || (q > 0 && L.filter_times[q] <= L.filter_times[q - 1]))
+          return fail(DFB_ERR_INVALID, "on_times: indices must be non-negative and strictly increasing");
+    }
   }
   if (p.trace_every < 0 || p.trace_capacity < 0 || p.event_capacity < 0 || p.ring_capacity < 0)
     return fail(DFB_ERR_INVALID, "negative capacity");

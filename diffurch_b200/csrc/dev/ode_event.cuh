@@ -59,10 +59,13 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
 
   size_t gid;
   double aux[NA];
-  double cj[I > 1 ? I - 1 : 1][N];  // FAST: pre-combined interpolant of the parked step
+  // FAST: the pre-combined interpolant of the parked step overwrites k[1 .. I-1] (the stages are
+  // dead once a lane is parked: the event re-step recomputes them and only k[0] = d_prev is needed
+  // for the undo), so parking adds no loop-carried registers
   double last_call[NLOC], sep_prev[NLOC];
   int every_i[NLOC];
   uint32_t has_last_call, status;
+  bool combined;  // k[1 .. I-1] of the step in flight already hold the interpolant coefficients
   unsigned n_steps, n_events, n_evlog, n_samples;
   unsigned long long n_rhs, on_step_calls;
 
@@ -78,7 +81,9 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
   // ---- interpolant of the step in flight (State::eval, state.rs:83-92) ------------------
   __device__ __forceinline__ void precombine() {
     if (!FAST) return;
+    static_assert(!FAST || I <= S, "the interpolant coefficients are stored in k[1 .. I-1]");
     const double t_step = t_curr - t_prev;
+    double c[I > 1 ? I - 1 : 1][N];
 #pragma unroll
     for (int j = 1; j < I; ++j)
 #pragma unroll
@@ -86,9 +91,14 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
         double acc = 0.0;
 #pragma unroll
         for (int i = 0; i < S; ++i) acc = fma(k()[i][n], A.bi[i * DFB_MAX_INTERP + j], acc);
-        cj[j - 1][n] = acc * t_step;
+        c[j - 1][n] = acc * t_step;
       }
+#pragma unroll
+    for (int j = 1; j < I; ++j)
+#pragma unroll
+      for (int n = 0; n < N; ++n) k()[j][n] = c[j - 1][n];
   }
+  __device__ __forceinline__ double cj(int j, int n) { return k()[j + 1][n]; }
   template <int D>
   __device__ __forceinline__ void eval_in_step(double t, double* out) {
     const double t_step = t_curr - t_prev;
@@ -96,9 +106,9 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
     if (FAST && D == 0) {
 #pragma unroll
       for (int n = 0; n < N; ++n) {
-        double acc = cj[I - 2][n];
+        double acc = cj(I - 2, n);
 #pragma unroll
-        for (int j = I - 3; j >= 0; --j) acc = fma(acc, theta, cj[j][n]);
+        for (int j = I - 3; j >= 0; --j) acc = fma(acc, theta, cj(j, n));
         out[n] = fma(acc, theta, p_prev()[n]);
       }
     } else {
@@ -233,7 +243,8 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
     if (L.dedup && ((has_last_call >> l) & 1u) && !(t_prev > last_call[l])) return false;
     if (!detect_base(L)) return false;
     if (L.filter == DFB_FILTER_SEPARATED_BY || L.filter == DFB_FILTER_IN_INTERVAL) {
-      precombine();  // FilterLocated::detect locates at once (rare: filtered locators only)
+      if (!combined) precombine();  // FilterLocated::detect locates at once (rare: filtered locators only)
+      combined = true;
       return filter_pass(L, l, locate_base(L));
     }
     if (L.filter == DFB_FILTER_EVERY || L.filter == DFB_FILTER_ON_TIMES) return filter_pass(L, l, t_curr);
@@ -284,6 +295,7 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
     t_curr = t_prev = A.t0;
     has_last_call = 0u;
     status = 0u;
+    combined = false;
 #pragma unroll
     for (int l = 0; l < NLOC; ++l) {
       last_call[l] = 0.0;
@@ -341,10 +353,13 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
       if (stepping == 0u && parked == 0u) break;  // every lane is done and the ensemble is exhausted
 
       // (1) batched event location (HListLocateEarliest, loc.rs:821-835)
-      if (parked != 0u && (stepping == 0u || __popc(parked) >= A.locate_batch || parked_iters >= A.locate_wait)) {
+      const bool locate_round =
+          parked != 0u && (stepping == 0u || __popc(parked) >= A.locate_batch || parked_iters >= A.locate_wait);
+      if (locate_round) {
         parked_iters = 0;
         if (mode == MODE_LOCATE) {
-          precombine();
+          if (!combined) precombine();
+          combined = true;
           bool found = false;
           double best_t = 0.0;
           int best_i = 0;
@@ -376,12 +391,13 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
             mode = next_mode();
           }
         }
-        continue;
+      } else if (parked != 0u) {
+        ++parked_iters;
       }
-      if (parked != 0u) ++parked_iters;
 
-      // (2) one make_step for every lane that can advance
-      if (mode == MODE_STEP || mode == MODE_EVENT_RESTEP) {
+      // (2) one make_step for every lane that can advance (not in a location round: the lanes
+      // that just located join the next round's step together with everybody else)
+      if (!locate_round && (mode == MODE_STEP || mode == MODE_EVENT_RESTEP)) {
         const bool restep = mode == MODE_EVENT_RESTEP;
         const double h_req = restep ? (ev_time - t_curr) : fmin(A.h, A.t1 - t_curr);
         if (t_prev == t_curr) {  // state.rs:97-98: make_step evaluates k[0] itself
@@ -389,6 +405,7 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
           ++n_rhs;
         }
         this->template step<false>(h_req);
+        combined = false;
         n_rhs += S;
         if (restep) {
           // solver.rs:304-309: commit; zero step; callback of the located event; commit
@@ -438,8 +455,11 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
   }
 };
 
+#ifndef DFB_EV_MINB
+#define DFB_EV_MINB(N) ((N) <= 2 ? 4 : 3)
+#endif
 template <class Sys, int S, int I, unsigned long long AMASK, unsigned BMASK, bool FAST, int NLOC, int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, DFB_EV_MINB(Sys::N))
     ode_event_kernel(const __grid_constant__ OdeFixedArgs A) {
   OdeEventStepper<Sys, S, I, AMASK, BMASK, FAST, NLOC> st(A);
   st.run();

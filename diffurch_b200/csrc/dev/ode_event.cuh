@@ -82,17 +82,23 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
   __device__ __forceinline__ void precombine() {
     if (!FAST) return;
     static_assert(!FAST || I <= S, "the interpolant coefficients are stored in k[1 .. I-1]");
+    // y(t) = p_prev + sum_j c_j (t - t_prev)^j with c_j = h sum_i k_i bi[i][j] / h^j: the division
+    // theta = (t - t_prev) / h of rk.rs/state.rs:85 is paid once per event, not once per iteration
     const double t_step = t_curr - t_prev;
+    const double inv = 1.0 / t_step;
+    double scale = 1.0;  // h / h^j
     double c[I > 1 ? I - 1 : 1][N];
 #pragma unroll
-    for (int j = 1; j < I; ++j)
+    for (int j = 1; j < I; ++j) {
 #pragma unroll
       for (int n = 0; n < N; ++n) {
         double acc = 0.0;
 #pragma unroll
         for (int i = 0; i < S; ++i) acc = fma(k()[i][n], A.bi[i * DFB_MAX_INTERP + j], acc);
-        c[j - 1][n] = acc * t_step;
+        c[j - 1][n] = acc * scale;
       }
+      scale *= inv;
+    }
 #pragma unroll
     for (int j = 1; j < I; ++j)
 #pragma unroll
@@ -101,17 +107,18 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
   __device__ __forceinline__ double cj(int j, int n) { return k()[j + 1][n]; }
   template <int D>
   __device__ __forceinline__ void eval_in_step(double t, double* out) {
-    const double t_step = t_curr - t_prev;
-    const double theta = (t - t_prev) / t_step;
     if (FAST && D == 0) {
+      const double s = t - t_prev;
 #pragma unroll
       for (int n = 0; n < N; ++n) {
         double acc = cj(I - 2, n);
 #pragma unroll
-        for (int j = I - 3; j >= 0; --j) acc = fma(acc, theta, cj(j, n));
-        out[n] = fma(acc, theta, p_prev()[n]);
+        for (int j = I - 3; j >= 0; --j) acc = fma(acc, s, cj(j, n));
+        out[n] = fma(acc, s, p_prev()[n]);
       }
     } else {
+      const double t_step = t_curr - t_prev;
+      const double theta = (t - t_prev) / t_step;
       dense_output<D, N>(Tab{A.bi}, p_prev(), t_step, theta, k(), out);
     }
   }

@@ -8,10 +8,11 @@
 //
 //     y(t) = y_r + sum_{j=1}^{I-1} d_j (t - t_r)^j ,   d_j = sum_i k_i * bi[i][j] / h^(j-1)
 //
-// i.e. (t_r, y_r[N], d_1[N] .. d_{I-1}[N]) = 8 (1 + N I) bytes (48 B for N = 1, I = 5),
-// into a per-trajectory ring in HBM laid out [slot][warp][field][lane]: every
-// access of a warp is one fully coalesced 256-byte row, and one warp's record is a
-// contiguous 8(1 + N I) x 32-byte block.  A lookup is then one
+// i.e. (y_r[N], d_1[N] .. d_{I-1}[N]) = 8 N I bytes (40 B for N = 1, I = 5) — the record's
+// start time t_r is NOT stored: with a fixed step the time grid is t_{r+1} = t_r + h and the
+// window below regenerates it bit for bit — into a per-trajectory ring in HBM laid out
+// [slot][warp][field][lane]: every access of a warp is one fully coalesced 256-byte row, and
+// one warp's record is a contiguous 8 N I x 32-byte block.  A lookup is then one
 // subtraction and an (I-1)-term Horner chain; y'(t) for neutral equations comes
 // from the same record.
 //
@@ -19,7 +20,7 @@
 // t + c_i h - tau, move monotonically through the history, so each thread keeps
 // the two records that bracket them (r0, r1) in registers plus a third (r2)
 // prefetched one step ahead; per step it stores one record and loads one:
-// 2 x 8(1 + N I) bytes of HBM traffic per RK step, which is the kernel's bound
+// 2 x 8 N I bytes of HBM traffic per RK step (80 B for N = 1, I = 5), which is the kernel's bound
 // (the ring of a 2^18-member ensemble is ~0.8 GB, far beyond L2).
 #pragma once
 #include "common.cuh"
@@ -50,7 +51,7 @@ struct DdeFixedArgs {
   unsigned long long* steps;
   unsigned long long* rhs_evals;
   uint32_t* status;
-  double* ring;  // [cap][ceil(n/32)][1 + N*I][32]
+  double* ring;  // [cap][ceil(n/32)][N*I][32]
 };
 
 // ---- cp.async (LDGSTS) helpers: global -> shared without staging registers; completion is
@@ -74,14 +75,14 @@ __device__ __forceinline__ void eval_staged(const double* p, double s, double* o
 #pragma unroll
   for (int n = 0; n < N; ++n) {
     if (D == 0) {
-      double acc = p[32 * (1 + N * (I - 1) + n)];
+      double acc = p[32 * (N * (I - 1) + n)];
 #pragma unroll
-      for (int j = I - 2; j >= 1; --j) acc = fma(acc, s, p[32 * (1 + N * j + n)]);
-      out[n] = fma(acc, s, p[32 * (1 + n)]);
+      for (int j = I - 2; j >= 1; --j) acc = fma(acc, s, p[32 * (N * j + n)]);
+      out[n] = fma(acc, s, p[32 * n]);
     } else {
-      double acc = double(I - 1) * p[32 * (1 + N * (I - 1) + n)];
+      double acc = double(I - 1) * p[32 * (N * (I - 1) + n)];
 #pragma unroll
-      for (int j = I - 2; j >= 1; --j) acc = fma(acc, s, double(j) * p[32 * (1 + N * j + n)]);
+      for (int j = I - 2; j >= 1; --j) acc = fma(acc, s, double(j) * p[32 * (N * j + n)]);
       out[n] = acc;
     }
   }
@@ -123,16 +124,15 @@ struct DdeFixedStepper {
   static constexpr int N = Sys::N;
   static constexpr int I_ = I;
   static constexpr int NP = Sys::NP > 0 ? Sys::NP : 1;
-  static constexpr int F = 1 + N * I;       // doubles per record
-  static constexpr int FP = F + (F & 1);    // padded to an even count: 16-byte cp.async chunks
-  static constexpr int kWarpRec = FP * 32;  // doubles of one warp's record block
+  static constexpr int F = N * I;          // doubles per record
+  static constexpr int kWarpRec = F * 32;  // doubles of one warp's record block (F x 256 bytes)
 
   const DdeFixedArgs& A;
   size_t gid;
   size_t g_thread;  // global thread index (= trajectory index for valid lanes)
   bool valid;
   int lane;
-  double* sm;  // this warp's staging area [kDdeSmemSlots][FP][32]
+  double* sm;  // this warp's staging area [kDdeSmemSlots][F][32]
   double t_curr, t_prev;
   double p_curr[N], p_prev[N], d_curr[N];
   double k[S][N];
@@ -146,7 +146,7 @@ struct DdeFixedStepper {
   int w;
   uint32_t status;
   bool loaded, uniform;
-  unsigned warp_base, slot_stride;  // ring addressing in doubles: [slot][warp][FP][32] (host guarantees < 2^32)
+  unsigned warp_base, slot_stride;  // ring addressing in doubles: [slot][warp][F][32] (host guarantees < 2^32)
 
   __device__ DdeFixedStepper(const DdeFixedArgs& A_, size_t g_, size_t gid_, bool valid_, double* sm_)
       : A(A_), gid(gid_), g_thread(g_), valid(valid_), lane(int(threadIdx.x & 31)), sm(sm_) {}
@@ -209,9 +209,9 @@ struct DdeFixedStepper {
   }
 
   // ---- ring I/O: [slot][warp][field][lane] -----------------------------------
-  // One warp's record is a contiguous FP x 256-byte block: every field access is one
+  // One warp's record is a contiguous F x 256-byte block: every field access is one
   // fully coalesced row, field offsets are compile-time immediates, and the block moves
-  // to shared memory with FP/2 16-byte cp.async per lane.
+  // to shared memory as F x 16 16-byte cp.async chunks (F/2 per lane, + half a warp if F is odd).
   __device__ __forceinline__ double* warp_block(int rec) const {
     const unsigned slot = unsigned(rec) & unsigned(A.ring_capacity - 1);
     return A.ring + (slot * slot_stride + warp_base);
@@ -223,7 +223,8 @@ struct DdeFixedStepper {
     const double* g = warp_block(rec);
     double* d = smem_block(rec);
 #pragma unroll
-    for (int q = 0; q < FP / 2; ++q) cp_async16(d + 2 * (lane + 32 * q), g + 2 * (lane + 32 * q));
+    for (int q = 0; q < F / 2; ++q) cp_async16(d + 2 * (lane + 32 * q), g + 2 * (lane + 32 * q));
+    if ((F & 1) && lane < 16) cp_async16(d + 2 * (lane + 32 * (F / 2)), g + 2 * (lane + 32 * (F / 2)));
   }
   // per-lane copy of one record (lanes of the warp disagree on the window position)
   __device__ __forceinline__ void copy_own_column(int rec) {
@@ -240,9 +241,8 @@ struct DdeFixedStepper {
   __device__ __forceinline__ void commit(int s, double t_step) {
     double inv = 1.0;  // 1 / h^(j-1) for partial steps
     double* p = warp_block(s) + lane;
-    __stcs(p, t_prev);
 #pragma unroll
-    for (int n = 0; n < N; ++n) __stcs(p + 32 * (1 + n), p_prev[n]);
+    for (int n = 0; n < N; ++n) __stcs(p + 32 * n, p_prev[n]);
 #pragma unroll
     for (int j = 1; j < I; ++j) {
 #pragma unroll
@@ -256,7 +256,7 @@ struct DdeFixedStepper {
           acc = first ? k[i][n] * cf : fma(k[i][n], cf, acc);
           first = false;
         }
-        __stcs(p + 32 * (1 + N * j + n), FULL ? acc : acc * inv);
+        __stcs(p + 32 * (N * j + n), FULL ? acc : acc * inv);
       }
       if (!FULL) inv = inv / t_step;
     }

@@ -54,11 +54,9 @@ bool launch_sys(int S, int I, unsigned long long am, unsigned bm, unsigned long 
 }
 }  // namespace
 
-// Doubles of ring the kernel needs per trajectory for (N, I, capacity); records are
-// padded to an even number of doubles (16-byte cp.async chunks).
+// Doubles of ring the kernel needs per trajectory for (N, I, capacity): N I per record.
 size_t dde_fixed_ring_doubles(int n_state, int I, int capacity) {
-  const int F = 1 + n_state * I;
-  return size_t(capacity) * size_t(F + (F & 1));
+  return size_t(capacity) * size_t(n_state * I);
 }
 
 // returns 0 = launched, >0 = CUDA error code, -1 = no compiled kernel

@@ -23,14 +23,18 @@ for r in rows:
             launch[-1][1].append((r[0], r[1].strip(), int(r[ie])))
         except ValueError:
             pass
+def opcode(sass):
+    m = re.match(r"(@!?U?P[0-9T]+\s+)?([A-Z][A-Z0-9_]*)", sass)
+    return m.group(2) if m else "?"
+
+
 name, L = launch[0]
 tot = sum(x[2] for x in L)
 print("kernel:", name[:120])
 print("warp instructions executed:", tot)
 op = collections.Counter()
 for _, s, n in L:
-    m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_]+)", s)
-    op[m.group(2)] += n
+    op[opcode(s)] += n
 print("opcode mix:", ", ".join(f"{k} {v / tot * 100:.1f}%" for k, v in op.most_common(14)))
 segs, cur = [], [L[0]]
 for x in L[1:]:
@@ -42,6 +46,6 @@ for x in L[1:]:
 segs.append(cur)
 for s in sorted(segs, key=lambda s: -sum(x[2] for x in s))[: int(sys.argv[2]) if len(sys.argv) > 2 else 6]:
     n = sum(x[2] for x in s)
-    ops = collections.Counter(re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_]+)", x[1]).group(2) for x in s)
+    ops = collections.Counter(opcode(x[1]) for x in s)
     print(f"  block @{s[0][0][-5:]}: {n / tot * 100:5.1f}% of executed, {len(s)} instrs x {s[0][2]:.3e}: "
           + ", ".join(f"{k} {v}" for k, v in ops.most_common(8)))

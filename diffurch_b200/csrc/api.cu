@@ -737,6 +737,10 @@ int dfb_run(dfb_handle* h, void* stream_v) {
   P.event_capacity = h->d_ev_t ? p.event_capacity : 0;
   P.ring_capacity = h->ring_capacity;
   P.uses_disco = h->uses_disco ? 1 : 0;
+  // pre-combined history records need b_i(0) = 0 for every stage (true of every rk.rs tableau)
+  P.coeff_records = (p.arith == DFB_ARITH_FAST && h->info.uses_history && !std::getenv("DFB_NO_COEFF_RECORDS")) ? 1 : 0;
+  for (int i = 0; i < p.rk.S && P.coeff_records; ++i)
+    if (p.rk.bi[i * DFB_MAX_INTERP] != 0.0) P.coeff_records = 0;
   P.max_steps = p.max_steps;
   P.n_traj = n;
   P.y0 = y0;

@@ -38,7 +38,7 @@ struct DevProblem {
   int32_t stepsize_kind;
   int32_t trace_every, trace_capacity, event_capacity, ring_capacity;
   int32_t uses_disco;  // any PROPAGATION locator or initial_disco entry
-  int32_t _pad;
+  int32_t coeff_records;  // FAST: history records hold pre-combined interpolant coefficients (integrator.cuh)
   long long max_steps;
   size_t n_traj;
   // inputs (SoA, trajectory index fastest)

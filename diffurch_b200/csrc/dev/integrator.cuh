@@ -85,9 +85,19 @@ __device__ __forceinline__ void dense_output(const Tab& tab, const double* y_pre
 // StateHistory (state.rs:11-23, 161-187) over a per-trajectory ring in HBM.
 // Ring record r holds (t_r, y_r) and the stages k of the step that ENDED at
 // t_r, i.e. k_deque[r-1] of the reference.
+//
+// Two things differ from the reference's VecDeque without changing what a lookup returns:
+//  * the partition point (first record with t_r > t, state.rs:165) is found from a per-lane
+//    HINT — the record the previous lookup landed in — by a short linear probe, falling back to
+//    the binary search only when the probe runs long.  Delayed arguments move monotonically, so a
+//    lookup costs ~2 loads of the time column instead of log2(len) dependent ones.  Same index as
+//    the binary search (the column is sorted), so STRICT results are unchanged bit for bit;
+//  * FAST arithmetic with `P->coeff_records`: the k slots of a record hold the pre-combined
+//    coefficients of the step's interpolant, d_j = sum_i k_i bi[i][j] / h^(j-1) (j = 1..I-1), as in
+//    dev/dde_fixed.cuh: a lookup loads N I doubles instead of N (1 + S) and is a Horner chain.
 template <int N, class Tab, bool ENABLED>
 struct History {
-  static constexpr int S = Tab::S;
+  static constexpr int S = Tab::S, I = Tab::I;
   const DevProblem* P;
   Tab tab;
   size_t gid;
@@ -95,6 +105,8 @@ struct History {
   uint32_t status;
   double y0[N];
   double hist_k;  // parameter of the sin history functions
+  int base = 0;   // records pruned so far: absolute index of ring record 0
+  int hint = 0;   // absolute index of the partition point of the previous lookup
 
   __device__ __forceinline__ size_t slot(int r) const {
     return size_t((head + r) & (P->ring_capacity - 1));
@@ -105,6 +117,46 @@ struct History {
   template <int D>
   __device__ void init_eval(double t, double* out) {
     init_condition_eval<D, N>(P->history_id, t, y0, hist_k, status, out);
+  }
+
+  // VecDeque::partition_point(|t_i| t_i <= t): first record with t_r > t
+  __device__ __forceinline__ int partition_point(double t) {
+    int r = hint - base;
+    r = r < 0 ? 0 : (r > len ? len : r);
+    int lo = 0, hi = len;
+    int probes = 0;
+    bool settled = false;
+    // forward while t_r <= t, backward while t_{r-1} > t; at most 8 probes in total
+    while (probes < 8) {
+      if (r < len && T(r) <= t) {
+        lo = ++r;
+        ++probes;
+      } else {
+        hi = r;
+        break;
+      }
+    }
+    if (probes < 8) {
+      while (probes < 8) {
+        if (r > lo && !(T(r - 1) <= t)) {
+          hi = --r;
+          ++probes;
+        } else {
+          settled = true;
+          break;
+        }
+      }
+    }
+    if (!settled) {  // the hint was far off (first lookup, state-dependent delay): bisect [lo, hi)
+      while (lo < hi) {
+        const int mid = lo + (hi - lo) / 2;
+        if (T(mid) <= t) lo = mid + 1;
+        else hi = mid;
+      }
+      r = lo;
+    }
+    hint = base + r;
+    return r;
   }
 
   template <int D>
@@ -119,13 +171,7 @@ struct History {
       status |= DFB_TRAJ_HISTORY_NOT_READY;
       return;
     }
-    // VecDeque::partition_point(|t_i| t_i <= t)
-    int lo = 0, hi = len;
-    while (lo < hi) {
-      const int mid = lo + (hi - lo) / 2;
-      if (T(mid) <= t) lo = mid + 1;
-      else hi = mid;
-    }
+    const int lo = partition_point(t);
     if (lo == 0 || lo == len) {
       status |= (lo == 0) ? DFB_TRAJ_HISTORY_DELETED : DFB_TRAJ_HISTORY_NOT_READY;
 #pragma unroll
@@ -135,6 +181,29 @@ struct History {
     const size_t n_traj = P->n_traj;
     const size_t s0 = slot(lo - 1), s1 = slot(lo);
     const double t_prev = P->ring_t[s0 * n_traj + gid];
+#if DFB_ARITH == 1
+    if (P->coeff_records) {
+      const double s = t - t_prev;
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        double d[I > 1 ? I - 1 : 1];
+#pragma unroll
+        for (int j = 0; j < I - 1; ++j) d[j] = P->ring_k[((s1 * S + j) * N + n) * n_traj + gid];
+        if (D == 0) {
+          double acc = d[I - 2];
+#pragma unroll
+          for (int j = I - 3; j >= 0; --j) acc = fma(acc, s, d[j]);
+          out[n] = fma(acc, s, P->ring_y[(s0 * N + n) * n_traj + gid]);
+        } else {
+          double acc = double(I - 1) * d[I - 2];
+#pragma unroll
+          for (int j = I - 3; j >= 0; --j) acc = fma(acc, s, double(j + 1) * d[j]);
+          out[n] = acc;
+        }
+      }
+      return;
+    }
+#endif
     const double t_next = P->ring_t[s1 * n_traj + gid];
     double y_prev[N];
     double k[S][N];
@@ -149,12 +218,13 @@ struct History {
     dense_output<D, N>(tab, y_prev, t_step, theta, k, out);
   }
 
-  // push of commit_step (state.rs:123-125)
-  __device__ void push(double t, const double* y, const double (*k)[N]) {
+  // push of commit_step (state.rs:123-125); t_step = length of the step that ended at t
+  __device__ void push(double t, const double* y, const double (*k)[N], double t_step) {
     if (!ENABLED) return;
     if (len == P->ring_capacity) {  // library limit, not a reference behaviour
       head = (head + 1) & (P->ring_capacity - 1);
       --len;
+      ++base;
       status |= DFB_TRAJ_RING_OVERFLOW;
     }
     const size_t n_traj = P->n_traj;
@@ -163,6 +233,25 @@ struct History {
 #pragma unroll
     for (int n = 0; n < N; ++n) P->ring_y[(s * N + n) * n_traj + gid] = y[n];
     if (k) {
+#if DFB_ARITH == 1
+      if (P->coeff_records) {
+        const double inv = 1.0 / t_step;  // zero-length commits (solver.rs:308) give NaN records nobody reads
+        double scale = 1.0;               // 1 / h^(j-1)
+#pragma unroll
+        for (int j = 1; j < I; ++j) {
+#pragma unroll
+          for (int n = 0; n < N; ++n) {
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < S; ++i) acc = fma(k[i][n], tab.bi(i, j), acc);
+            P->ring_k[((s * S + (j - 1)) * N + n) * n_traj + gid] = acc * scale;
+          }
+          scale *= inv;
+        }
+        ++len;
+        return;
+      }
+#endif
 #pragma unroll
       for (int i = 0; i < S; ++i)
 #pragma unroll
@@ -176,6 +265,7 @@ struct History {
     while (len > 1 && T(1) < t_tail) {
       head = (head + 1) & (P->ring_capacity - 1);
       --len;
+      ++base;
     }
   }
 };
@@ -330,7 +420,7 @@ struct Integrator {
 
   // State::commit_step (state.rs:122-139)
   __device__ void commit_step() {
-    hist.push(t_curr, p_curr, k);
+    hist.push(t_curr, p_curr, k, t_curr - t_prev);
     const double t_tail = t_prev - P.max_delay;
     hist.prune(t_tail);
     if (P.uses_disco) disco.prune(t_tail);
@@ -594,7 +684,7 @@ struct Integrator {
     for (int i = 0; i < S; ++i)
 #pragma unroll
       for (int n = 0; n < N; ++n) k[i][n] = 0.0;
-    hist.push(P.t0, p0, nullptr);
+    hist.push(P.t0, p0, nullptr, 0.0);
     if (P.uses_disco)
       for (int i = 0; i < P.n_disco; ++i) disco.push(P.disco_t[i], P.disco_order[i]);
     h_auto = P.automatic.stepsize;

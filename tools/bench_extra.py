@@ -34,6 +34,15 @@ def timed(make, reps=2):
             "steps_per_s": tot["steps"] / (ms * 1e-3), "events_per_s": tot["events"] / (ms * 1e-3)}
 
 
+def relay_clamp(n, arith):
+    # examples/dde-relay-clamp.rs:19-36 as an ensemble over alpha (DDE + propagation + located events)
+    alpha = np.linspace(3.0, 7.0, n)
+    prm = np.stack([alpha, np.full(n, 0.4), np.full(n, 1.0)], axis=1)
+    y0 = np.stack([np.ones(n), -alpha], axis=1)
+    return (d.Solver.new().initial(y0).equation(d.systems.DdeRelayClamp, prm).interval(0.0, 30.0).stepsize(0.012)
+            .with_const_delay(1.0, 2).on(d.Locator.zero("abs_delayed_x_minus_1"), None).arith(arith))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the BASELINE ensemble sizes")
@@ -50,6 +59,10 @@ def main():
         "lyapunov_lorenz_2^16_rho_grid_t100_fast": lambda: cases.lyap_lorenz(100.0, rho=np.linspace(20.0, 40.0, n_ly), arith="fast"),
         "lorenz_2^20_adaptive_fast": lambda: cases.lorenz(n=n_lo, t1=50.0, arith="fast").stepsize(
             d.AutomaticStepsize(1e-2, (1e-6, 1e-1), [1e-9] * 3, [1e-9] * 3, 4, 0.9, (0.2, 5.0))),
+        "dde_relay_clamp_2^16_t30_fast": lambda: relay_clamp(n_ly, "fast"),
+        "dde_relay_clamp_2^16_t30_strict": lambda: relay_clamp(n_ly, "strict"),
+        "lorenz_2^16_adaptive_with_events_fast": lambda: cases.lorenz(n=n_ly, t1=20.0, arith="fast").stepsize(
+            d.AutomaticStepsize(1e-2, (1e-6, 1e-1), [1e-9] * 3, [1e-9] * 3, 4, 0.9, (0.2, 5.0))).on(d.Periodic(0.5, 0.0), None),
         "lorenz_2^20_rk4_fast": lambda: cases.lorenz(n=n_lo, t1=50.0, arith="fast", rk=d.RK.rk4()),
         "lorenz_2^20_rktp64_strict": lambda: cases.lorenz(n=n_lo, t1=50.0, arith="strict"),
     }

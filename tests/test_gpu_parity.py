@@ -856,3 +856,52 @@ def test_full_size_linearity_property():
                         .interval(0.0, 2.0).stepsize(0.01).arith(arith))
         g1, g4 = mk(1.0).run(), mk(4.0).run()
         assert np.array_equal(g1.p * 4.0, g4.p)
+
+
+def test_full_size_bouncing_ball_properties():
+    # BASELINE configs[3] at full size: 2^19 members, x0 = 1 + i/n, t in [0, 8], FAST arithmetic.
+    # Between impacts the flight is a parabola that rktp64 integrates exactly up to rounding, so the
+    # impact times are known in closed form: t_1 = (v0 + sqrt(v0^2 + 2 g x0)) / g, then the flight
+    # times shrink by the restitution factor k = 0.9.
+    n = 1 << 19
+    g = cases.bouncing_ball(n=n, t1=8.0, arith="fast", events=8).run()
+    assert g.totals["kernel_kind"] == d.abi.KERNEL_ODE_EVENT and g.totals["n_failed"] == 0
+    x0 = 1.0 + np.arange(n) / n
+    v0, grav, k = -0.01, 9.8, 0.9
+    impacts = g.event_t[np.arange(n), np.argmax(g.event_index[:, :8] == 1, axis=1)]   # first "bounce" event
+    t1 = (v0 + np.sqrt(v0 * v0 + 2.0 * grav * x0)) / grav
+    assert np.max(np.abs(impacts - t1)) < 1e-12
+    # number of impacts before t = 8: t_m = t_1 + (2 v_1 / g) k (1 - k^(m-1)) / (1 - k), v_1 = sqrt(v0^2 + 2 g x0)
+    v1 = np.sqrt(v0 * v0 + 2.0 * grav * x0)
+    m = np.arange(1, 200)[None, :]
+    tm = t1[:, None] + (2.0 * v1[:, None] / grav) * k * (1.0 - k ** (m - 1)) / (1.0 - k)
+    n_imp = (tm < 8.0).sum(axis=1)
+    apex = g.events.astype(np.int64) - n_imp          # the no-op `zero(dx)` locator fires once per flight
+    assert np.all(np.abs(apex - n_imp) <= 1)
+    assert np.all(g.p[:, 0] > -1e-9) and np.all(np.abs(g.t - 8.0) < 1e-12)
+
+
+def test_full_size_egg_billiard_properties():
+    # 2^19 members, 200 reflections each: the flow between reflections is free flight and a
+    # reflection is an isometry of the velocity, so speed is conserved; the ball stays in the egg.
+    n = 1 << 19
+    g = cases.egg_billiard(n=n, reflections=200, arith="fast", events=0).run()
+    assert g.totals["kernel_kind"] == d.abi.KERNEL_ODE_EVENT and g.totals["n_failed"] == 0
+    assert np.all(g.status == d.abi.TRAJ_STOPPED) and np.all(g.events == 200) and np.all(g.aux[:, 0] == 200.0)
+    speed = np.hypot(g.p[:, 2], g.p[:, 3])
+    assert np.max(np.abs(speed - 0.5)) < 1e-12
+    x, y = g.p[:, 0], g.p[:, 1]
+    assert np.max(np.abs(x * x + y * y - y ** 3 / 3.0 - 1.0)) < 1e-9   # stopped ON the boundary
+
+
+def test_full_size_lyapunov_batch_properties():
+    # BASELINE configs[4]: 2^16-member rho grid; the exponents sum to the trace of the Jacobian,
+    # -(sigma + 1 + beta), for every member; the leading one is positive on the chaotic band
+    n, tmax = 1 << 16, 50.0
+    rho = np.linspace(24.0, 40.0, n)
+    g = cases.lyap_lorenz(tmax, rho=rho, arith="fast").run()
+    assert g.totals["kernel_kind"] == d.abi.KERNEL_ODE_FIXED_PERIODIC and g.totals["n_failed"] == 0
+    lam = g.aux / tmax
+    assert np.max(np.abs(lam.sum(axis=1) + (10.0 + 1.0 + 8.0 / 3.0))) < 1e-6
+    assert np.all(g.events == 100) and np.all(g.steps == g.steps[0])
+    assert np.mean(lam[:, 0] > 0.3) > 0.9

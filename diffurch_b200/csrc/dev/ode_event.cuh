@@ -402,59 +402,71 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
         ++parked_iters;
       }
 
-      // (2) one make_step for every lane that can advance (not in a location round: the lanes
-      // that just located join the next round's step together with everybody else)
-      if (!locate_round && (mode == MODE_STEP || mode == MODE_EVENT_RESTEP)) {
-        const bool restep = mode == MODE_EVENT_RESTEP;
-        const double h_req = restep ? (ev_time - t_curr) : fmin(A.h, A.t1 - t_curr);
-        if (t_prev == t_curr) {  // state.rs:97-98: make_step evaluates k[0] itself
-          Sys::rhs(view_curr(), prm(), d_curr());
-          ++n_rhs;
-        }
-        this->template step<false>(h_req);
-        combined = false;
-        n_rhs += S;
-        if (restep) {
-          // solver.rs:304-309: commit; zero step; callback of the located event; commit
-          t_prev = t_curr;
+      // (2) make_step rounds for every lane that can advance (not in a location round: the lanes
+      // that just located join the next round's step together with everybody else).  Up to
+      // A.inner_steps rounds run back to back before the warp votes again: lanes that park or
+      // finish inside the burst idle for at most inner_steps - 1 rounds (they would wait for the
+      // batch anyway), and the vote / batching / refill logic is paid once per burst.
+      if (!locate_round) {
+#pragma unroll 1
+        for (int it = 0; it < A.inner_steps; ++it) {
+          if (it > 0) {
+            if (__ballot_sync(0xffffffffu, mode == MODE_STEP || mode == MODE_EVENT_RESTEP) == 0u) break;
+            if (parked != 0u) ++parked_iters;
+          }
+          if (mode == MODE_STEP || mode == MODE_EVENT_RESTEP) {
+            const bool restep = mode == MODE_EVENT_RESTEP;
+            const double h_req = restep ? (ev_time - t_curr) : fmin(A.h, A.t1 - t_curr);
+            if (t_prev == t_curr) {  // state.rs:97-98: make_step evaluates k[0] itself
+              Sys::rhs(view_curr(), prm(), d_curr());
+              ++n_rhs;
+            }
+            this->template step<false>(h_req);
+            combined = false;
+            n_rhs += S;
+            if (restep) {
+              // solver.rs:304-309: commit; zero step; callback of the located event; commit
+              t_prev = t_curr;
 #pragma unroll
-          for (int n = 0; n < N; ++n) p_prev()[n] = p_curr()[n];
+              for (int n = 0; n < N; ++n) p_prev()[n] = p_curr()[n];
 #pragma unroll
-          for (int l = 0; l < NLOC; ++l) {
-            if (l == ev_index) {
-              const dfb_locator& L = A.loc[l];
-              if (L.dedup) {  // DedupLocF::eval_mut (loc.rs:1023-1026)
-                has_last_call |= 1u << l;
-                last_call[l] = t_curr;
+              for (int l = 0; l < NLOC; ++l) {
+                if (l == ev_index) {
+                  const dfb_locator& L = A.loc[l];
+                  if (L.dedup) {  // DedupLocF::eval_mut (loc.rs:1023-1026)
+                    has_last_call |= 1u << l;
+                    last_call[l] = t_curr;
+                  }
+                  if (L.callback_id != DFB_CB_NONE) {
+                    RefMut m{&t_curr, p_curr(), d_curr(), t_prev, p_prev(), &this->nohist};
+                    Sys::callback(L.callback_id, m, prm(), aux);
+                  }
+                }
               }
-              if (L.callback_id != DFB_CB_NONE) {
-                RefMut m{&t_curr, p_curr(), d_curr(), t_prev, p_prev(), &this->nohist};
-                Sys::callback(L.callback_id, m, prm(), aux);
+              ++n_events;
+              if (A.event_capacity > 0) {
+                if (n_evlog < uint32_t(A.event_capacity)) {
+                  A.ev_t[size_t(n_evlog) * A.n_traj + gid] = ev_time;
+                  A.ev_idx[size_t(n_evlog) * A.n_traj + gid] = ev_index;
+                }
+                ++n_evlog;
+              }
+              ++n_steps;
+              on_step();
+              mode = next_mode();
+            } else {
+              fired_mask = 0u;
+#pragma unroll
+              for (int l = 0; l < NLOC; ++l)
+                if (l < A.n_loc && detect_phase(A.loc[l], l)) fired_mask |= 1u << l;
+              if (fired_mask != 0u) {
+                mode = MODE_LOCATE;
+              } else {
+                ++n_steps;  // commit_step
+                on_step();
+                mode = next_mode();
               }
             }
-          }
-          ++n_events;
-          if (A.event_capacity > 0) {
-            if (n_evlog < uint32_t(A.event_capacity)) {
-              A.ev_t[size_t(n_evlog) * A.n_traj + gid] = ev_time;
-              A.ev_idx[size_t(n_evlog) * A.n_traj + gid] = ev_index;
-            }
-            ++n_evlog;
-          }
-          ++n_steps;
-          on_step();
-          mode = next_mode();
-        } else {
-          fired_mask = 0u;
-#pragma unroll
-          for (int l = 0; l < NLOC; ++l)
-            if (l < A.n_loc && detect_phase(A.loc[l], l)) fired_mask |= 1u << l;
-          if (fired_mask != 0u) {
-            mode = MODE_LOCATE;
-          } else {
-            ++n_steps;  // commit_step
-            on_step();
-            mode = next_mode();
           }
         }
       }

@@ -53,6 +53,7 @@ struct OdeFixedArgs {
   long long max_steps;
   unsigned long long* queue;     // work counter (zeroed before the launch)
   int32_t locate_batch, locate_wait;
+  int32_t inner_steps;           // step rounds between two warp votes (>= 1)
   int32_t trace_every, trace_capacity;
   double* trace_t;               // [cap][n]
   double* trace_y;               // [cap][N][n]

@@ -4,6 +4,7 @@
 #include "dev/ode_event.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace DFB_NS {
@@ -113,6 +114,8 @@ int run_ode_event_shim(int system_id, const dfb_tableau& rk, double t0, double t
   A.queue = queue;
   A.locate_batch = locate_batch;
   A.locate_wait = locate_wait;
+  A.inner_steps = 4;
+  if (const char* e = std::getenv("DFB_EVENT_INNER")) A.inner_steps = std::atoi(e) > 0 ? std::atoi(e) : 1;
   return launch_ode_event(system_id, rk.S, rk.I, A, n_sm, stream);
 }
 

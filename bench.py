@@ -189,7 +189,7 @@ def other_config_legs(d, peak_tflops):
     after one warm-up, kernel time from the library's CUDA events (dfb_totals.kernel_ms)."""
     import cases
     KIND = {0: "integrate_general_kernel", 1: "ode_fixed_kernel", 2: "dde_fixed_kernel",
-            3: "ode_adaptive_kernel", 4: "ode_fixed_periodic_kernel"}
+            3: "ode_adaptive_kernel", 4: "ode_fixed_periodic_kernel", 5: "ode_event_kernel"}
 
     def timed(make):
         ens = make().build()
@@ -413,8 +413,8 @@ def main():
 
     # ---- CPU baseline (oracle "port"), bounded sample on this box's host cores ----
     cores = os.cpu_count() or 1
-    probe_rate, _, _ = cpu_oracle_rate(256 * cores, cores)       # sizes the sample for ~12 s of CPU work
-    n_sample = int(max(1024 * cores, min(N_MEMBERS, 12.0 * probe_rate / STEPS_PER_MEMBER)))
+    probe_rate, _, _ = cpu_oracle_rate(256 * cores, cores)       # sizes the sample for ~15 s of CPU work
+    n_sample = int(max(1024 * cores, min(N_MEMBERS, 15.0 * probe_rate / STEPS_PER_MEMBER)))
     n_sample -= n_sample % cores
     cpu_rate, cpu_dt, _ = cpu_oracle_rate(n_sample, cores)
     cpu1_rate, _, _ = cpu_oracle_rate(64, 1)

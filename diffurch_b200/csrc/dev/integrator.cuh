@@ -82,6 +82,47 @@ __device__ __forceinline__ void dense_output(const Tab& tab, const double* y_pre
   }
 }
 
+// Partition point of a ring's time column (first record with t_r > t), started from `r`:
+// forward while t_r <= t, backward while t_{r-1} > t, at most 8 probes, then bisection of what
+// is left.  One out-of-line copy serves every lookup site of a kernel (the lookups of the stages,
+// the detectors and the bisection iterations would otherwise each inline it).
+static __device__ __noinline__ int history_partition_point(const double* t_col, size_t n_traj, int head, int mask,
+                                                    int len, int r, double t) {
+  auto T = [&](int q) { return t_col[size_t((head + q) & mask) * n_traj]; };
+  int lo = 0, hi = len;
+  int probes = 0;
+  bool settled = false;
+  while (probes < 8) {
+    if (r < len && T(r) <= t) {
+      lo = ++r;
+      ++probes;
+    } else {
+      hi = r;
+      break;
+    }
+  }
+  if (probes < 8) {
+    while (probes < 8) {
+      if (r > lo && !(T(r - 1) <= t)) {
+        hi = --r;
+        ++probes;
+      } else {
+        settled = true;
+        break;
+      }
+    }
+  }
+  if (!settled) {  // the start was far off (first lookup, state-dependent delay): bisect [lo, hi)
+    while (lo < hi) {
+      const int mid = lo + (hi - lo) / 2;
+      if (T(mid) <= t) lo = mid + 1;
+      else hi = mid;
+    }
+    r = lo;
+  }
+  return r;
+}
+
 // StateHistory (state.rs:11-23, 161-187) over a per-trajectory ring in HBM.
 // Ring record r holds (t_r, y_r) and the stages k of the step that ENDED at
 // t_r, i.e. k_deque[r-1] of the reference.
@@ -123,38 +164,7 @@ struct History {
   __device__ __forceinline__ int partition_point(double t) {
     int r = hint - base;
     r = r < 0 ? 0 : (r > len ? len : r);
-    int lo = 0, hi = len;
-    int probes = 0;
-    bool settled = false;
-    // forward while t_r <= t, backward while t_{r-1} > t; at most 8 probes in total
-    while (probes < 8) {
-      if (r < len && T(r) <= t) {
-        lo = ++r;
-        ++probes;
-      } else {
-        hi = r;
-        break;
-      }
-    }
-    if (probes < 8) {
-      while (probes < 8) {
-        if (r > lo && !(T(r - 1) <= t)) {
-          hi = --r;
-          ++probes;
-        } else {
-          settled = true;
-          break;
-        }
-      }
-    }
-    if (!settled) {  // the hint was far off (first lookup, state-dependent delay): bisect [lo, hi)
-      while (lo < hi) {
-        const int mid = lo + (hi - lo) / 2;
-        if (T(mid) <= t) lo = mid + 1;
-        else hi = mid;
-      }
-      r = lo;
-    }
+    r = history_partition_point(P->ring_t + gid, P->n_traj, head, P->ring_capacity - 1, len, r, t);
     hint = base + r;
     return r;
   }

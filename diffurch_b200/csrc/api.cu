@@ -205,7 +205,6 @@ struct dfb_handle {
   unsigned launches = 0;
   int locate_batch = 32;     // lanes parked on a detected event before the warp runs its bisections
   int locate_max_wait = 16;  // ... or step rounds the first parked lane has waited (DFB_LOCATE_WAIT)
-  bool used_hot_path = false;
   uint32_t kernel_kind = DFB_KERNEL_GENERAL;
 };
 
@@ -383,7 +382,9 @@ int dfb_register_plugin(const char* so_path, int32_t* system_id_out) {
   }
   dfb_plugin_desc d;
   std::memset(&d, 0, sizeof(d));
-  if (describe(&d) != 0 || d.plugin_abi != DFB_PLUGIN_ABI) {
+  if (describe(&d) != 0 || d.plugin_abi != DFB_PLUGIN_ABI || d.sizeof_devproblem != sizeof(DevProblem) ||
+      d.sizeof_locator != sizeof(dfb_locator) || d.sizeof_tableau != sizeof(dfb_tableau) ||
+      d.sizeof_auto_stepsize != sizeof(dfb_auto_stepsize)) {
     dlclose(dl);
     return fail(DFB_ERR_INVALID, "plugin ABI mismatch: rebuild it with diffurch_b200.user.build_user_system");
   }
@@ -597,7 +598,6 @@ int dfb_run(dfb_handle* h, void* stream_v) {
   const bool hot_eligible = p.stepsize_kind == DFB_STEP_FIXED && p.n_loc == 0 &&
                             !h->info.uses_history && p.trace_every == 0 && p.max_steps == 0 &&
                             p.history_id == DFB_HIST_CONSTANT && !std::getenv("DFB_FORCE_GENERAL");
-  h->used_hot_path = false;
   h->kernel_kind = DFB_KERNEL_GENERAL;
   if (hot_eligible) {
     DFB_CUDA(cudaMemsetAsync(h->d_rejected, 0, n * sizeof(unsigned long long), stream));
@@ -611,7 +611,6 @@ int dfb_run(dfb_handle* h, void* stream_v) {
     if (rc == 0) {
       DFB_CUDA(cudaEventRecord(h->ev1, stream));
       h->launches = 1;
-      h->used_hot_path = true;
       h->kernel_kind = DFB_KERNEL_ODE_FIXED;
       h->ran = true;
       return DFB_OK;
@@ -637,7 +636,6 @@ int dfb_run(dfb_handle* h, void* stream_v) {
     if (rc == 0) {
       DFB_CUDA(cudaEventRecord(h->ev1, stream));
       h->launches = 1;
-      h->used_hot_path = true;
       h->kernel_kind = DFB_KERNEL_ODE_FIXED_PERIODIC;
       h->ran = true;
       return DFB_OK;
@@ -665,7 +663,6 @@ int dfb_run(dfb_handle* h, void* stream_v) {
     if (rc == 0) {
       DFB_CUDA(cudaEventRecord(h->ev1, stream));
       h->launches = 1;
-      h->used_hot_path = true;
       h->kernel_kind = DFB_KERNEL_ODE_EVENT;
       h->ran = true;
       return DFB_OK;
@@ -690,7 +687,6 @@ int dfb_run(dfb_handle* h, void* stream_v) {
     if (rc == 0) {
       DFB_CUDA(cudaEventRecord(h->ev1, stream));
       h->launches = 1;
-      h->used_hot_path = true;
       h->kernel_kind = DFB_KERNEL_ODE_ADAPTIVE;
       h->ran = true;
       return DFB_OK;
@@ -709,7 +705,6 @@ int dfb_run(dfb_handle* h, void* stream_v) {
     if (rc < 0) return fail(DFB_ERR_UNSUPPORTED, "no DDE hot-path kernel for this tableau");
     DFB_CUDA(cudaEventRecord(h->ev1, stream));
     h->launches = 1;
-    h->used_hot_path = true;
     h->kernel_kind = DFB_KERNEL_DDE_FIXED;
     h->ran = true;
     return DFB_OK;

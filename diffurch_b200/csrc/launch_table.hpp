@@ -70,11 +70,13 @@ struct DfbLaunchTable {
   }
 
 // What a plugin's `dfb_plugin_describe` fills in (csrc/plugin_entry.cu).
-#define DFB_PLUGIN_ABI 1
+#define DFB_PLUGIN_ABI 2
 struct dfb_plugin_desc {
   int plugin_abi;
   int n_state, n_params, n_aux, n_detectors, n_callbacks, uses_history;
   int dde_hot_ok;  // constant-delay system the coefficient-ring kernel can take
+  // layout check of every struct that crosses the plugin boundary by reference
+  unsigned sizeof_devproblem, sizeof_locator, sizeof_tableau, sizeof_auto_stepsize;
   const char* name;
   DfbLaunchTable fast, strict;
 };

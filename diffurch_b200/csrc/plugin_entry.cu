@@ -38,6 +38,10 @@ extern "C" __attribute__((visibility("default"))) int dfb_plugin_describe(dfb_pl
   out->n_callbacks = Sys::NC;
   out->uses_history = Sys::uses_history ? 1 : 0;
   out->dde_hot_ok = (Sys::uses_history && Sys::has_const_delay) ? 1 : 0;
+  out->sizeof_devproblem = unsigned(sizeof(DevProblem));
+  out->sizeof_locator = unsigned(sizeof(dfb_locator));
+  out->sizeof_tableau = unsigned(sizeof(dfb_tableau));
+  out->sizeof_auto_stepsize = unsigned(sizeof(dfb_auto_stepsize));
   out->name = DFB_STR(DFB_PLUGIN_SYSTEM);
   out->fast = DfbLaunchTable{dfb_fast::run_ode_fixed_shim, dfb_fast::run_ode_fixed_periodic_shim,
                              dfb_fast::run_ode_event_shim, dfb_fast::run_ode_adaptive_shim,

@@ -74,6 +74,20 @@ def build_user_system(header, struct_name, out_dir=None, force=False, verbose=Fa
     return so
 
 
+def build_user_system_from_source(source, struct_name, out_dir, **kw):
+    """Same as :func:`build_user_system` for functor code held in a string (e.g. generated from a
+    symbolic right-hand side): the text is written to ``<out_dir>/<struct_name>.cuh`` first.  It may
+    omit the ``#include "user_system.cuh"`` / ``namespace DFB_NS`` wrapper."""
+    os.makedirs(out_dir, exist_ok=True)
+    if "user_system.cuh" not in source:
+        source = '#include "user_system.cuh"\nnamespace DFB_NS {\n' + source + "\n}  // namespace DFB_NS\n"
+    path = os.path.join(out_dir, struct_name + ".cuh")
+    if not os.path.exists(path) or open(path).read() != source:
+        with open(path, "w") as f:
+            f.write(source)
+    return build_user_system(path, struct_name, out_dir=os.path.join(out_dir, "_build"), **kw)
+
+
 def load_user_system(so_path, name=None, params=(), detectors=None, callbacks=None, reference=""):
     """Register a plugin built by :func:`build_user_system`; returns the `System` descriptor that
     ``Solver.equation`` takes.  `params`, `detectors` and `callbacks` name the functor's parameter

@@ -177,6 +177,7 @@ struct dfb_handle {
   int device = 0;
   int ring_capacity = 0;
   bool uses_disco = false;
+  bool ode_history = false;  // ODE + a RegulaFalsi locator: keep the reference's retained steps (integrator.cuh)
   bool has_initial = false, has_params = false, ran = false;
   // inputs
   double *d_y0 = nullptr, *d_params = nullptr;
@@ -432,6 +433,9 @@ int dfb_create(const dfb_problem* desc, size_t n_traj, int device, dfb_handle** 
   for (int l = 0; l < desc->n_loc; ++l)
     if (desc->loc[l].kind == DFB_LOC_PROPAGATION) h->uses_disco = true;
   if (desc->n_disco > 0) h->uses_disco = true;
+  for (int l = 0; l < desc->n_loc; ++l)
+    if (!info->uses_history && desc->loc[l].kind == DFB_LOC_STATEFN && desc->loc[l].location == DFB_LOCATE_REGULA_FALSI)
+      h->ode_history = true;
 
   const size_t n = n_traj;
   const int N = info->n_state, S = desc->rk.S;
@@ -497,7 +501,7 @@ int dfb_create(const dfb_problem* desc, size_t n_traj, int device, dfb_handle** 
     cap = next_pow2(cap);
     h->ring_capacity = int(cap);
     H_ALLOC(h->d_ring_coeff, ((n + 31) / 32 * 32) * dfb_fast::dde_fixed_ring_doubles(N, desc->rk.I, int(cap)));
-  } else if (info->uses_history) {
+  } else if (info->uses_history || h->ode_history) {
     size_t cap = size_t(desc->ring_capacity);
     if (cap == 0) {
       // window of the reference's deque: ceil(max_delay / h) + 3 records, plus two
@@ -644,7 +648,7 @@ int dfb_run(dfb_handle* h, void* stream_v) {
 
   // Fixed step + located events (dev/ode_event.cuh): state-function and Periodic locators, ODE only.
   bool event_eligible = p.stepsize_kind == DFB_STEP_FIXED && p.n_loc > 0 && !h->info.uses_history &&
-                        p.history_id == DFB_HIST_CONSTANT && !std::getenv("DFB_FORCE_GENERAL");
+                        p.history_id == DFB_HIST_CONSTANT && !h->ode_history && !std::getenv("DFB_FORCE_GENERAL");
   for (int l = 0; l < p.n_loc && event_eligible; ++l)
     event_eligible = p.loc[l].kind == DFB_LOC_STATEFN || p.loc[l].kind == DFB_LOC_PERIODIC;
   if (event_eligible) {
@@ -732,6 +736,7 @@ int dfb_run(dfb_handle* h, void* stream_v) {
   P.event_capacity = h->d_ev_t ? p.event_capacity : 0;
   P.ring_capacity = h->ring_capacity;
   P.uses_disco = h->uses_disco ? 1 : 0;
+  P.ode_history = h->ode_history ? 1 : 0;
   // pre-combined history records need b_i(0) = 0 for every stage (true of every rk.rs tableau)
   P.coeff_records = (p.arith == DFB_ARITH_FAST && h->info.uses_history && !std::getenv("DFB_NO_COEFF_RECORDS")) ? 1 : 0;
   for (int i = 0; i < p.rk.S && P.coeff_records; ++i)

@@ -35,10 +35,18 @@ __device__ __forceinline__ double dev_powi(double a, int b) {
 }
 
 // Tableau accessor over the kernel parameter block, compile-time shape.
-template <int S_, int I_>
+// RT = run-time shape: the kernel is instantiated for the maximal shape (S_, I_ = array sizes and
+// unroll bounds) and every stage / interpolant loop iteration is additionally guarded by the
+// tableau's own S and I.  One such instantiation per system is the catch-all that makes every
+// (system, tableau) pair runnable; the exact-shape instantiations (RT = false) are the fast ones.
+template <int S_, int I_, bool RT_ = false>
 struct ParamTab {
   static constexpr int S = S_, I = I_;
+  static constexpr bool RT = RT_;
   const dfb_tableau& t;
+  __device__ __forceinline__ bool stage(int i) const { return !RT || i < t.S; }
+  __device__ __forceinline__ bool term(int j) const { return !RT || j < t.I; }
+  __device__ __forceinline__ int s_rt() const { return RT ? t.S : S; }
   __device__ __forceinline__ double a(int i, int j) const { return t.a[i * DFB_MAX_STAGES + j]; }
   __device__ __forceinline__ double b(int j) const { return t.b[j]; }
   __device__ __forceinline__ double b2(int j) const { return t.b2[j]; }
@@ -62,13 +70,16 @@ __device__ __forceinline__ void dense_output(const Tab& tab, const double* y_pre
   for (int n = 0; n < N; ++n) delta[n] = 0.0;
 #pragma unroll
   for (int i = 0; i < S; ++i) {
+    if (!tab.stage(i)) continue;
     double b_i = 0.0;
     if (D == 0) {
 #pragma unroll
-      for (int j = 0; j < I; ++j) b_i += tab.bi(i, j) * pw[j];
+      for (int j = 0; j < I; ++j)
+        if (tab.term(j)) b_i += tab.bi(i, j) * pw[j];
     } else {
 #pragma unroll
-      for (int j = 1; j < I; ++j) b_i += tab.bi(i, j) * pw[j - 1] * double(j);
+      for (int j = 1; j < I; ++j)
+        if (tab.term(j)) b_i += tab.bi(i, j) * pw[j - 1] * double(j);
     }
 #pragma unroll
     for (int n = 0; n < N; ++n) delta[n] += k[i][n] * b_i;
@@ -196,20 +207,21 @@ struct History {
       const double s = t - t_prev;
 #pragma unroll
       for (int n = 0; n < N; ++n) {
+        const size_t Sr = size_t(tab.s_rt());
         double d[I > 1 ? I - 1 : 1];
 #pragma unroll
-        for (int j = 0; j < I - 1; ++j) d[j] = P->ring_k[((s1 * S + j) * N + n) * n_traj + gid];
-        if (D == 0) {
-          double acc = d[I - 2];
+        for (int j = 0; j < I - 1; ++j)
+          d[j] = tab.term(j + 1) ? P->ring_k[((s1 * Sr + j) * N + n) * n_traj + gid] : 0.0;
+        double acc = 0.0;
+        bool started = false;
 #pragma unroll
-          for (int j = I - 3; j >= 0; --j) acc = fma(acc, s, d[j]);
-          out[n] = fma(acc, s, P->ring_y[(s0 * N + n) * n_traj + gid]);
-        } else {
-          double acc = double(I - 1) * d[I - 2];
-#pragma unroll
-          for (int j = I - 3; j >= 0; --j) acc = fma(acc, s, double(j + 1) * d[j]);
-          out[n] = acc;
+        for (int j = I - 2; j >= 0; --j) {
+          if (!tab.term(j + 1)) continue;
+          const double c = D == 0 ? d[j] : double(j + 1) * d[j];
+          acc = started ? fma(acc, s, c) : c;
+          started = true;
         }
+        out[n] = D == 0 ? fma(acc, s, P->ring_y[(s0 * N + n) * n_traj + gid]) : acc;
       }
       return;
     }
@@ -222,7 +234,8 @@ struct History {
 #pragma unroll
     for (int i = 0; i < S; ++i)
 #pragma unroll
-      for (int n = 0; n < N; ++n) k[i][n] = P->ring_k[((s1 * S + i) * N + n) * n_traj + gid];
+      for (int n = 0; n < N; ++n)
+        k[i][n] = tab.stage(i) ? P->ring_k[((s1 * size_t(tab.s_rt()) + i) * N + n) * n_traj + gid] : 0.0;
     const double t_step = t_next - t_prev;
     const double theta = (t - t_prev) / t_step;
     dense_output<D, N>(tab, y_prev, t_step, theta, k, out);
@@ -249,12 +262,14 @@ struct History {
         double scale = 1.0;               // 1 / h^(j-1)
 #pragma unroll
         for (int j = 1; j < I; ++j) {
+          if (!tab.term(j)) continue;
 #pragma unroll
           for (int n = 0; n < N; ++n) {
             double acc = 0.0;
 #pragma unroll
-            for (int i = 0; i < S; ++i) acc = fma(k[i][n], tab.bi(i, j), acc);
-            P->ring_k[((s * S + (j - 1)) * N + n) * n_traj + gid] = acc * scale;
+            for (int i = 0; i < S; ++i)
+              if (tab.stage(i)) acc = fma(k[i][n], tab.bi(i, j), acc);
+            P->ring_k[((s * size_t(tab.s_rt()) + (j - 1)) * N + n) * n_traj + gid] = acc * scale;
           }
           scale *= inv;
         }
@@ -265,7 +280,8 @@ struct History {
 #pragma unroll
       for (int i = 0; i < S; ++i)
 #pragma unroll
-        for (int n = 0; n < N; ++n) P->ring_k[((s * S + i) * N + n) * n_traj + gid] = k[i][n];
+        for (int n = 0; n < N; ++n)
+          if (tab.stage(i)) P->ring_k[((s * size_t(tab.s_rt()) + i) * N + n) * n_traj + gid] = k[i][n];
     }
     ++len;
   }
@@ -320,14 +336,19 @@ struct DiscoList {
 
 enum : int { MODE_STEP = 0, MODE_EVENT_RESTEP = 1, MODE_LOCATE = 2, MODE_DONE = 3 };
 
-template <class Sys, int S, int I, bool HAS_LOC>
+// ODEHIST: keep the delay-history ring for a system that never looks anything up itself.  The
+// reference stores the last two steps even for ODEs (commit_step with max_delay = 0 keeps three
+// records, state.rs:122-133), and `State::eval` falls back to them for a time outside the step in
+// flight (state.rs:83-92).  Only the RegulaFalsi location method can ask for such a time (its secant
+// may leave the bracket, loc.rs:260-285), so only problems that use it pay for the ring.
+template <class Sys, int S, int I, bool HAS_LOC, bool RT = false, bool ODEHIST = false>
 struct Integrator {
   static constexpr int N = Sys::N;
   static constexpr int NP = Sys::NP > 0 ? Sys::NP : 1;
   static constexpr int NA = Sys::NA > 0 ? Sys::NA : 1;
   static constexpr int MAXL = HAS_LOC ? DFB_MAX_LOCATORS : 1;
-  using Tab = ParamTab<S, I>;
-  using Hist = History<N, Tab, Sys::uses_history>;
+  using Tab = ParamTab<S, I, RT>;
+  using Hist = History<N, Tab, Sys::uses_history || ODEHIST>;
   using Ref = StateRef<N, Hist>;
   using RefMut = StateRefMut<N, Hist>;
 
@@ -398,6 +419,7 @@ struct Integrator {
     }
 #pragma unroll
     for (int i = 1; i < S; ++i) {
+      if (!tab.stage(i)) continue;
       t_curr = t_prev + tab.c(i) * t_step;
 #pragma unroll
       for (int n = 0; n < N; ++n) {
@@ -412,7 +434,8 @@ struct Integrator {
     for (int n = 0; n < N; ++n) {
       double acc = 0.0;
 #pragma unroll
-      for (int j = 0; j < S; ++j) acc = acc + k[j][n] * tab.b(j);
+      for (int j = 0; j < S; ++j)
+        if (tab.stage(j)) acc = acc + k[j][n] * tab.b(j);
       p_curr[n] = p_prev[n] + acc * t_step;
     }
     t_curr = t_prev + t_step;
@@ -422,7 +445,8 @@ struct Integrator {
       for (int n = 0; n < N; ++n) {
         double acc = 0.0;
 #pragma unroll
-        for (int j = 0; j < S; ++j) acc = acc + k[j][n] * (tab.b2(j) - tab.b(j));
+        for (int j = 0; j < S; ++j)
+          if (tab.stage(j)) acc = acc + k[j][n] * (tab.b2(j) - tab.b(j));
         e_curr[n] = acc * t_step;
       }
     }
@@ -866,13 +890,13 @@ struct Integrator {
   }
 };
 
-template <class Sys, int S, int I, bool HAS_LOC>
+template <class Sys, int S, int I, bool HAS_LOC, bool RT = false, bool ODEHIST = false>
 __global__ void __launch_bounds__(128)
     integrate_general_kernel(const __grid_constant__ DevProblem P, int locate_batch_threshold,
                              int locate_max_wait) {
   const size_t gid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool valid = gid < P.n_traj;
-  Integrator<Sys, S, I, HAS_LOC> it(P, valid ? gid : 0);
+  Integrator<Sys, S, I, HAS_LOC, RT, ODEHIST> it(P, valid ? gid : 0);
   it.run(valid, locate_batch_threshold, locate_max_wait);
 }
 

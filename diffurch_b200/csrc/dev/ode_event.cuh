@@ -45,6 +45,8 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
     static constexpr int S = S_, I = I_;
     const double* v;
     __device__ __forceinline__ double bi(int i, int j) const { return v[i * DFB_MAX_INTERP + j]; }
+    __device__ __forceinline__ bool stage(int) const { return true; }  // exact shape (see ParamTab)
+    __device__ __forceinline__ bool term(int) const { return true; }
   };
   using Base::A;
   using Base::t_curr;

@@ -248,6 +248,9 @@ void run_one(const RunArgs& A, size_t i) {
     y_fin = st.p_curr;
     rhs_evals = st.rhs_evals;
     if (std::isinf(t_fin)) status |= TRAJ_STOPPED;  // stop_integration (state_fn.rs:92-97)
+    // library status, not a reference behaviour: the reference returns the non-finite state silently
+    for (int k = 0; k < N; ++k)
+      if (!(std::fabs(y_fin[k]) < std::numeric_limits<double>::infinity())) status |= TRAJ_NONFINITE;
   } catch (const Panic& p) {
     status |= p.status;
   }

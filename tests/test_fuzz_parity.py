@@ -1,0 +1,274 @@
+"""Randomised parity: seeded random Solver configurations, CUDA path (whatever kernel the
+dispatcher picks) against the CPU oracle on the same inputs.
+
+STRICT arithmetic must be BIT-IDENTICAL for systems without transcendental calls: final state,
+times, step / event / rhs-evaluation counters, status words, event logs (bisection results) and
+traces.  Every case prints its seed and configuration on failure; kernel kinds seen are
+collected so the run also shows the dispatcher reached every ODE kernel family.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import diffurch_b200 as d
+from diffurch_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+RK_NAMES = ["euler", "midpoint", "heun2", "ralston2", "kutta3", "heun3", "ralston3", "wray3", "ssp3", "rk4",
+            "three_eights", "rk43", "rktp64"]
+SEEN = set()
+
+
+def pick_rk(rng):
+    r = rng.integers(0, len(RK_NAMES) + 4)
+    if r < len(RK_NAMES):
+        return d.RK.by_name(RK_NAMES[r]), RK_NAMES[r]
+    if r == len(RK_NAMES):
+        c2 = float(rng.uniform(0.2, 1.0))
+        return d.RK.generic_order_2(c2), f"generic_order_2({c2})"
+    if r == len(RK_NAMES) + 1:
+        c2, c3 = float(rng.uniform(0.2, 0.6)), float(rng.uniform(0.65, 1.0))
+        return d.RK.generic_order_3(c2, c3), f"generic_order_3({c2},{c3})"
+    return d.RK.rktp64(), "rktp64"      # the default tableau gets extra weight
+
+
+PANIC_BITS = abi.TRAJ_HISTORY_DELETED | abi.TRAJ_HISTORY_NOT_READY | abi.TRAJ_NO_DERIVATIVE
+
+
+def same(g, o, what=""):
+    # a member the reference would have panicked on has no final State upstream: the oracle leaves
+    # NaN there, the device path leaves the state at the moment of the panic; everything else
+    # (status word, counters up to the panic, event log, trace) must still agree
+    alive = (o.status & PANIC_BITS) == 0
+    for name in ("t", "p", "aux", "rhs_evals"):   # (the oracle reads its rhs counter off the returned State)
+        x, y = getattr(g, name), getattr(o, name)
+        if x is None or y is None or not np.size(x):
+            continue
+        assert np.array_equal(x[alive], y[alive], equal_nan=True), f"{name} differs {what}"
+    for name in ("steps", "rejected", "events", "status"):
+        x, y = getattr(g, name), getattr(o, name)
+        if x is None or y is None or not np.size(x):
+            continue
+        assert np.array_equal(x, y, equal_nan=True), f"{name} differs {what}"
+    if g.event_n is not None:
+        assert np.array_equal(g.event_n, o.event_n), f"event_n differs {what}"
+        assert np.array_equal(g.event_t, o.event_t, equal_nan=True), f"event times differ {what}"
+        assert np.array_equal(g.event_index, o.event_index), f"event indices differ {what}"
+    if g.trace_n is not None:
+        assert np.array_equal(g.trace_n, o.trace_n), f"trace_n differs {what}"
+        for i in range(len(g.trace_n)):
+            n = int(g.trace_n[i])
+            assert np.array_equal(g.trace_t[i, :n], o.trace_t[i, :n]), f"trace t differs (member {i}) {what}"
+            assert np.array_equal(g.trace_p[i, :n], o.trace_p[i, :n], equal_nan=True), f"trace p differs {what}"
+
+
+def ode_system(rng, n):
+    """(system, params, y0, t0) of a random transcendental-free ODE system."""
+    k = rng.integers(0, 6)
+    if k == 0:
+        rho = rng.uniform(5.0, 40.0, n)
+        return d.systems.Lorenz, np.stack([np.full(n, 10.0), rho, np.full(n, 8.0 / 3.0)], 1), \
+            rng.uniform(-5, 5, (n, 3)) + [0, 0, 20], 0.0
+    if k == 1:
+        return d.systems.Harmonic, None, rng.uniform(-2, 2, (n, 2)), float(rng.uniform(-1, 1))
+    if k == 2:
+        return d.systems.Linear1, rng.uniform(-2, 1, (n, 1)), rng.uniform(0.5, 2, (n, 1)), 0.0
+    if k == 3:
+        return d.systems.Linear3, rng.uniform(-1, 1, (n, 9)), rng.uniform(-1, 1, (n, 3)), 0.0
+    if k == 4:
+        return d.systems.Time3, None, rng.uniform(-1, 1, (n, 3)), float(rng.uniform(0, 2))
+    return d.systems.Linear3Matrix, rng.uniform(-1, 1, (n, 9)), np.tile(np.eye(3).reshape(1, 9), (n, 1)), 0.0
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_fixed_step_ode_strict_bit_exact(oracle, seed):
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 130))
+    system, prm, y0, t0 = ode_system(rng, n)
+    rk, rk_name = pick_rk(rng)
+    h = float(rng.choice([0.5, 0.1, 0.03, 1.0 / 64, 0.0123456789]))
+    t1 = t0 + float(rng.uniform(0.0, 40.0)) * h * (1 if rng.random() < 0.9 else 0)   # sometimes an empty interval
+    trace = d.Trace(int(rng.integers(1, 5)), 64) if rng.random() < 0.4 else None
+    periodic = rng.random() < 0.35 and system in (d.systems.Linear1, d.systems.Linear3Matrix)
+
+    def mk():
+        s = d.Solver.new().initial(y0).interval(t0, t1).stepsize(h).rk(rk).arith("strict")
+        s = s.equation(system, prm) if prm is not None else s.equation(system)
+        if trace is not None:
+            s = s.on_step(trace)
+        if periodic:
+            cb = "renormalize" if system is d.systems.Linear1 else "qr_ln_abs"
+            s = s.on_mut(d.Periodic(float(rng_period), float(rng_offset)), cb)
+        return s
+    rng_period, rng_offset = rng.uniform(2.0, 9.0) * h, rng.uniform(0.0, 1.0) * h
+    what = f"[seed {seed}: {system.name} n={n} rk={rk_name} h={h} t=[{t0},{t1}] trace={trace is not None} periodic={periodic}]"
+    g = mk().run()
+    o = oracle.run_solver(mk(), n_threads=4)
+    SEEN.add(g.totals["kernel_kind"])
+    if system is d.systems.Linear3Matrix and periodic:
+        # the QR callback takes log(): compare the log sums to 1-2 ulp, everything else exactly
+        assert np.max(np.abs(g.aux - o.aux)) <= 1e-12 * (1.0 + np.max(np.abs(o.aux))), what
+        g.aux = o.aux
+    if system is d.systems.Linear1 and periodic:
+        assert np.max(np.abs(g.aux - o.aux)) <= 1e-12 * (1.0 + np.max(np.abs(o.aux))), what
+        g.aux = o.aux
+    same(g, o, what)
+
+
+DETECTIONS = [abi.DET_ZERO, abi.DET_ABOVE_ZERO, abi.DET_BELOW_ZERO, abi.DET_POSITIVE, abi.DET_NEGATIVE,
+              abi.DET_SWITCH, abi.DET_SWITCH_TRUE, abi.DET_SWITCH_FALSE, abi.DET_IS_TRUE, abi.DET_IS_FALSE,
+              abi.DET_STEP]
+LOCATIONS = [abi.LOCATE_STEP_BEGIN, abi.LOCATE_STEP_END, abi.LOCATE_STEP_MIDDLE, abi.LOCATE_LERP,
+             abi.LOCATE_BISECTION, abi.LOCATE_BISECTION_BOOL, abi.LOCATE_REGULA_FALSI]
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_fuzz_located_events_strict_bit_exact(oracle, seed):
+    rng = np.random.default_rng(5000 + seed)
+    n = int(rng.integers(1, 100))
+    which = rng.integers(0, 3)
+    rk, rk_name = (d.RK.rktp64(), "rktp64") if rng.random() < 0.6 else \
+        ((d.RK.rk43(), "rk43") if rng.random() < 0.5 else (d.RK.rk4(), "rk4"))
+    n_extra = int(rng.integers(0, 3))
+
+    def random_locator(det_name):
+        det = int(rng.choice(DETECTIONS))
+        # a boolean-valued detection goes with the boolean bisection, a sign detection with the real ones
+        boolean = det in (abi.DET_SWITCH, abi.DET_SWITCH_TRUE, abi.DET_SWITCH_FALSE, abi.DET_IS_TRUE, abi.DET_IS_FALSE)
+        if boolean:
+            loc = int(rng.choice([abi.LOCATE_STEP_BEGIN, abi.LOCATE_STEP_END, abi.LOCATE_BISECTION_BOOL]))
+        elif det in (abi.DET_POSITIVE, abi.DET_NEGATIVE, abi.DET_STEP):
+            loc = int(rng.choice([abi.LOCATE_STEP_BEGIN, abi.LOCATE_STEP_END]))
+        else:
+            loc = int(rng.choice([abi.LOCATE_STEP_BEGIN, abi.LOCATE_STEP_END, abi.LOCATE_LERP,
+                                  abi.LOCATE_BISECTION, abi.LOCATE_REGULA_FALSI]))
+        L = d.Locator._mk(det_name, det, loc)
+        f = rng.integers(0, 6)
+        if f == 1:
+            L = L.every(int(rng.integers(1, 4)))
+        elif f == 2:
+            L = L.separated_by(float(rng.uniform(0.1, 2.0)))
+        elif f == 3:
+            a = float(rng.uniform(0.0, 3.0))
+            L = L.in_interval(a, a + float(rng.uniform(0.5, 4.0)))
+        elif f == 4:
+            L = L.on_times(sorted(set(int(x) for x in rng.integers(0, 12, 4))))
+        return L, (det, loc, int(f))
+
+    descr = []
+    if which == 0:      # bouncing ball with its own two locators + random extras
+        y0 = np.stack([rng.uniform(0.5, 2.0, n), rng.uniform(-1.0, 1.0, n)], 1)
+        # restitution >= 0.85 and t <= 2 keep the run short of the Zeno time (t_1 + (2 v_1 / g) k / (1 - k)
+        # >= 3.9 for x0 >= 0.5), where the bounces accumulate and the reference itself never finishes
+        prm = np.tile([9.8, float(rng.uniform(0.85, 0.95))], (n, 1))
+        s0 = lambda: (d.Solver.new().initial(y0).equation(d.systems.BouncingBall, prm).interval(0.0, 2.0)
+                      .stepsize(float(h)).on(d.Locator.zero("dx"), None).on_mut(d.Locator.below_zero("x"), "bounce"))
+        h = rng.choice([0.005, 0.02, 0.05])
+        names = ["dx", "x"]
+    elif which == 1:    # relay with frozen sign
+        y0 = np.stack([rng.uniform(0.1, 1.0, n), rng.uniform(-0.5, 0.5, n)], 1)
+        s0 = lambda: (d.Solver.new().initial(y0).equation(d.systems.RelayMsign).interval(0.5, 8.5)
+                      .stepsize(float(h)).on(d.Locator.zero("x"), None))
+        h = rng.choice([0.09, 0.03, 0.2])
+        names = ["x"]
+    else:               # egg billiard
+        phi = rng.uniform(0, 2 * np.pi, n)
+        y0 = np.stack([np.zeros(n), np.full(n, 0.1), 0.5 * np.cos(phi), 0.5 * np.sin(phi)], 1)
+        prm = np.full((n, 1), float(rng.integers(3, 40)))
+        s0 = lambda: (d.Solver.new().initial(y0).equation(d.systems.EggBilliard, prm).interval(0.0, 60.0)
+                      .stepsize(float(h)).on_mut(d.Locator.above_zero("boundary"), "reflect"))
+        h = rng.choice([0.5, 0.25, 0.7])
+        names = ["boundary"]
+    extras = []
+    for _ in range(n_extra):
+        if rng.random() < 0.3:
+            extras.append((d.Periodic(float(rng.uniform(0.2, 1.5)), float(rng.uniform(0.0, 0.3))), ("periodic",)))
+        else:
+            extras.append(random_locator(str(rng.choice(names))))
+    use_trace = rng.random() < 0.5
+
+    def mk():
+        s = s0().rk(rk).arith("strict").log_events(d.EventLog(96)).max_steps(6000)   # guard: never spin
+        for L, _ in extras:
+            s = s.on(L, None)
+        if use_trace:
+            s = s.on_step(d.Trace(1, 1024))
+        return s
+    what = f"[seed {seed}: case {which} n={n} rk={rk_name} h={h} extras={[e[1] for e in extras]} trace={use_trace}]"
+    g = mk().run()
+    o = oracle.run_solver(mk(), n_threads=4)
+    SEEN.add(g.totals["kernel_kind"])
+    same(g, o, what)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_dde_strict_vs_oracle(oracle, seed):
+    # the sin history / exact solution put sin() on both sides: compare to 1e-13, counters exactly
+    rng = np.random.default_rng(9000 + seed)
+    n = int(rng.integers(1, 80))
+    k = rng.uniform(0.4, 1.4, n)
+    tau = float(rng.choice([1.0, 0.5, 0.73]))
+    h = float(rng.choice([0.02, 0.05, 0.011]))
+    rk, rk_name = [(d.RK.rktp64(), "rktp64"), (d.RK.rk43(), "rk43"), (d.RK.rk4(), "rk4")][rng.integers(0, 3)]
+    neutral = rng.random() < 0.4
+    import cases
+    if neutral:
+        prm, system, init = cases.ndde_params(k, tau), d.systems.NddeLinear, d.InitFn(d.SIN, d.SIN_DERIV)
+    else:
+        prm, system, init = cases.dde_params(k, tau), d.systems.DdeLinear, d.InitFn(d.SIN)
+    t1 = float(rng.uniform(1.0, 6.0))
+    for arith, tol in (("strict", 1e-13), ("fast", 1e-11)):
+        def mk():
+            return (d.Solver.new().max_delay(tau).initial(init).interval(0.0, t1).stepsize(h).rk(rk)
+                    .equation(system, prm).arith(arith))
+        g = mk().run()
+        o = oracle.run_solver(mk(), n_threads=4)
+        SEEN.add(g.totals["kernel_kind"])
+        what = f"[seed {seed}: {system.name} n={n} tau={tau} h={h} rk={rk_name} t1={t1} {arith}]"
+        assert np.array_equal(g.steps, o.steps) and np.array_equal(g.status, o.status), what
+        assert np.array_equal(g.t, o.t), what
+        assert np.max(np.abs(g.p - o.p)) < tol * max(1.0, float(np.max(np.abs(o.p)))), what
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_fuzz_adaptive_vs_oracle(oracle, seed):
+    # AutomaticStepsize: STRICT (general kernel, libm-like pow on both sides, <= 2 ulp apart) and FAST
+    # (ode_adaptive_kernel, Newton root) against the oracle: same step sequence up to one step near
+    # err = 1, states within the controller's tolerance
+    rng = np.random.default_rng(7000 + seed)
+    n = int(rng.integers(1, 150))
+    system, prm, y0, t0 = ode_system(rng, n)
+    if system is d.systems.Time3:
+        system, prm, y0, t0 = d.systems.Harmonic, None, rng.uniform(-2, 2, (n, 2)), 0.0
+    N = y0.shape[1]
+    tol = float(rng.choice([1e-6, 1e-8, 1e-10]))
+    rk, rk_name, order = [(d.RK.rktp64(), "rktp64", 4), (d.RK.rk43(), "rk43", 3), (d.RK.rk4(), "rk4", 2)][rng.integers(0, 3)]
+    ctl = d.AutomaticStepsize(stepsize=float(rng.choice([1e-2, 1e-3])), stepsize_range=(1e-9, 0.25), atol=[tol] * N,
+                              rtol=[tol] * N, order=order, fac=float(rng.uniform(0.8, 0.95)), fac_range=(0.2, 5.0))
+    t1 = t0 + float(rng.uniform(0.5, 3.0))
+
+    def mk(arith):
+        s = d.Solver.new().initial(y0).interval(t0, t1).stepsize(ctl).rk(rk).arith(arith)
+        return s.equation(system, prm) if prm is not None else s.equation(system)
+    o = oracle.run_solver(mk("strict"), n_threads=4)
+    what = f"[seed {seed}: {system.name} n={n} rk={rk_name} tol={tol} t=[{t0},{t1}]]"
+    for arith in ("strict", "fast"):
+        g = mk(arith).run()
+        SEEN.add(g.totals["kernel_kind"])
+        assert np.array_equal(g.status, o.status), what
+        ok = o.status == 0
+        assert np.max(np.abs(g.steps[ok].astype(np.int64) - o.steps[ok].astype(np.int64)), initial=0) <= 1, what
+        assert np.array_equal(g.t[ok], o.t[ok]), what
+        scale = np.maximum(np.abs(o.p[ok]), 1.0)
+        assert np.max(np.abs(g.p[ok] - o.p[ok]) / scale, initial=0.0) < 100 * tol, what
+
+
+def test_fuzz_reached_every_ode_kernel_family():
+    # runs last in this file: the random configurations above must have exercised these kernels
+    if not SEEN:
+        pytest.skip("fuzz cases did not run in this session")
+    assert {abi.KERNEL_ODE_FIXED, abi.KERNEL_ODE_EVENT, abi.KERNEL_GENERAL, abi.KERNEL_ODE_ADAPTIVE,
+            abi.KERNEL_DDE_FIXED}.issubset(SEEN), SEEN

@@ -266,6 +266,76 @@ def test_fuzz_adaptive_vs_oracle(oracle, seed):
         assert np.max(np.abs(g.p[ok] - o.p[ok]) / scale, initial=0.0) < 100 * tol, what
 
 
+@pytest.mark.parametrize("seed", range(16))
+def test_fuzz_dde_events_and_propagation_strict_bit_exact(oracle, seed):
+    # delay systems without transcendental calls, through the general kernel: the relay-clamp DDE
+    # (examples/dde-relay-clamp.rs) and y' = 0 with propagated discontinuities
+    # (tests/delay_propagation.rs), random delays / steps / tableaux / smoothing orders
+    rng = np.random.default_rng(11000 + seed)
+    n = int(rng.integers(1, 70))
+    rk, rk_name = [(d.RK.rktp64(), "rktp64"), (d.RK.rk43(), "rk43"), (d.RK.rk4(), "rk4"), (d.RK.euler(), "euler"),
+                   (d.RK.heun3(), "heun3")][rng.integers(0, 5)]
+    if rng.random() < 0.5:
+        T_ = float(rng.choice([1.0, 0.7, 1.3]))
+        alpha = rng.uniform(2.0, 7.0, n)
+        prm = np.stack([alpha, np.full(n, float(rng.uniform(0.1, 0.8))), np.full(n, T_)], 1)
+        y0 = np.stack([rng.uniform(0.5, 1.5, n), -alpha * rng.uniform(0.5, 1.5, n)], 1)
+        h = float(rng.choice([0.012, 0.05, 0.1])) * T_
+        smoothing = int(rng.integers(0, 3))
+
+        def mk():
+            s = (d.Solver.new().initial(y0).equation(d.systems.DdeRelayClamp, prm).interval(0.0, 8.0 * T_)
+                 .stepsize(h).rk(rk).with_const_delay(T_, smoothing).arith("strict").max_steps(5000)
+                 .log_events(d.EventLog(128)))
+            if rng_use_detector:
+                s = s.on(d.Locator.zero("abs_delayed_x_minus_1"), None)
+            return s
+        rng_use_detector = rng.random() < 0.7
+        what = f"[seed {seed}: relay clamp n={n} T={T_} h={h} rk={rk_name} smoothing={smoothing} det={rng_use_detector}]"
+    else:
+        delays = sorted(set(float(x) for x in rng.choice([0.5, 1.0, 1.25, 0.8], size=int(rng.integers(1, 3)))))
+        h = float(rng.choice([0.75, 7.0 / 8.0, 0.3, 0.123456789]))
+        discos = [(0.0, int(rng.integers(0, 2)))]
+        smoothing = int(rng.integers(0, 2))
+        pantograph = rng.random() < 0.3
+
+        def mk():
+            s = (d.Solver.new().rk(rk).initial(np.zeros((n, 1))).equation(d.systems.Zero1)
+                 .stepsize(h).arith("strict").max_steps(5000).on_step(d.Trace(1, 256)))
+            if pantograph:
+                return (s.initial_disco([(1.0, 0)]).interval(1.0, 40.0).with_delayed_argument("half_time", smoothing)
+                        .max_delay(math.inf))
+            s = s.initial_disco(discos).interval(0.0, 6.0)
+            for dl in delays:
+                s = s.with_const_delay(dl, smoothing)
+            return s
+        what = f"[seed {seed}: zero1 n={n} delays={delays} h={h} rk={rk_name} smoothing={smoothing} pantograph={pantograph}]"
+    g = mk().run()
+    o = oracle.run_solver(mk(), n_threads=4)
+    SEEN.add(g.totals["kernel_kind"])
+    same(g, o, what)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_fuzz_output_policies_and_ragged_sizes(oracle, seed):
+    # traces with `every` > 1 and a capacity smaller than the number of samples, event logs that
+    # overflow their capacity (the count keeps running), member counts around the warp / block edges
+    rng = np.random.default_rng(13000 + seed)
+    n = int(rng.choice([1, 2, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 257]))
+    every, cap, ecap = int(rng.integers(1, 7)), int(rng.integers(1, 40)), int(rng.integers(1, 5))
+    y0 = np.stack([rng.uniform(0.5, 2.0, n), rng.uniform(-1.0, 1.0, n)], 1)
+    prm = np.tile([9.8, 0.9], (n, 1))
+
+    def mk():
+        return (d.Solver.new().initial(y0).equation(d.systems.BouncingBall, prm).interval(0.0, 2.0)
+                .stepsize(0.01).on(d.Locator.zero("dx"), None).on_mut(d.Locator.below_zero("x"), "bounce")
+                .on_step(d.Trace(every, cap)).log_events(d.EventLog(ecap)).arith("strict").max_steps(3000))
+    g = mk().run()
+    o = oracle.run_solver(mk(), n_threads=4)
+    same(g, o, f"[seed {seed}: n={n} every={every} cap={cap} ecap={ecap}]")
+    assert np.all(g.trace_n <= cap)
+
+
 def test_fuzz_reached_every_ode_kernel_family():
     # runs last in this file: the random configurations above must have exercised these kernels
     if not SEEN:

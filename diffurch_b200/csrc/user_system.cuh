@@ -12,6 +12,11 @@
 //   };
 //   }  // namespace DFB_NS
 //
+// A callback may also WRITE the parameter block (`callback(int id, M& s, double* prm, double* aux)`):
+// that is how a parameter captured in a `Cell` by both the equation and a callback upstream is
+// restated (tests/plugins/switch_parameter.cuh).  Discrete mode variables of `#[state(discrete)]`
+// (macros/derive_state) are state components with a zero derivative, or aux slots.
+//
 // Optional members (defaults in SysBase): NA (aux accumulators), ND / NC (detector / callback
 // counts), `detector(id, view, prm)`, `callback(id, mut_view, prm, aux)`, `uses_history` +
 // `has_const_delay` + `const_delay(prm)` for delay equations, `pure_rhs = false` if rhs reads

@@ -3,7 +3,8 @@
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-PLUGINS = {"van_der_pol": "SysVanDerPol", "user_lorenz": "SysUserLorenz", "user_dde": "SysUserDde"}
+PLUGINS = {"van_der_pol": "SysVanDerPol", "user_lorenz": "SysUserLorenz", "user_dde": "SysUserDde",
+           "switch_parameter": "SysSwitchParameter"}
 
 
 def header(name):

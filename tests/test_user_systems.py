@@ -176,3 +176,39 @@ def test_van_der_pol_events_on_user_detector(built):
     assert abs(r.p[0, 0]) < 1e-12
     f = mk("fast").run()
     assert np.array_equal(f.events, s.events) and np.max(np.abs(f.event_t - s.event_t)) < 1e-10
+
+
+@pytest.mark.gpu
+def test_callback_may_switch_a_captured_parameter(built):
+    # examples/loc-switch-parameter.rs: gravity flips at every crossing of x = 0 (a `Cell` captured by
+    # the equation and the callback upstream; here the callback writes the parameter block)
+    sw = user.load_user_system(built["switch_parameter"], params=("g", "k"), detectors={"dx": 1, "x": 2},
+                               callbacks={"switch": 1})
+    n = 40
+    x0 = 1.0 + np.arange(n) / n
+    prm = np.tile([9.8, 0.9], (n, 1))
+
+    def mk(arith, t1=6.0):
+        return (d.Solver.new().initial(np.stack([x0, np.full(n, -0.01)], 1)).equation(sw, prm).interval(0.0, t1)
+                .stepsize(0.005).on(d.Locator.zero("dx"), None).on_mut(d.Locator.zero("x"), "switch")
+                .log_events(d.EventLog(128)).arith(arith))
+    s = mk("strict").run()
+    assert s.totals["kernel_kind"] == d.abi.KERNEL_ODE_EVENT and np.all(s.status == 0)
+    crossings = s.aux[:, 0]
+    assert np.all(crossings >= 3)
+    # first crossing = the free-fall time of the built-in bouncing ball; after it gravity points up,
+    # so the particle is below zero until the next crossing: sign(x) = (-1)^crossings
+    t1 = (-0.01 + np.sqrt(0.0001 + 2 * 9.8 * x0)) / 9.8
+    first = s.event_t[np.arange(n), np.argmax(s.event_index == 1, axis=1)]
+    assert np.max(np.abs(first - t1)) < 1e-13
+    assert np.all(np.sign(s.p[:, 0]) == (-1.0) ** crossings)
+    gen = None
+    os.environ["DFB_FORCE_GENERAL"] = "1"
+    try:
+        gen = mk("strict").run()
+    finally:
+        del os.environ["DFB_FORCE_GENERAL"]
+    assert gen.totals["kernel_kind"] == d.abi.KERNEL_GENERAL
+    assert np.array_equal(gen.p, s.p) and np.array_equal(gen.event_t, s.event_t) and np.array_equal(gen.aux, s.aux)
+    f = mk("fast").run()
+    assert np.array_equal(f.aux, s.aux) and np.max(np.abs(f.event_t - s.event_t)) < 1e-10

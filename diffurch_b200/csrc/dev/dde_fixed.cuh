@@ -43,6 +43,10 @@ struct DdeFixedArgs {
   double hc_min;          // min over stages i >= 1 of c_i * h (earliest delayed stage time of a step)
   int32_t history_id;
   int32_t ring_capacity;  // power of two
+  // full steps of length h that Solver::run takes before the closing partial step (solver.rs:292-293),
+  // counted on the host by replaying t += h with the same IEEE additions; < 0 = not counted (the
+  // kernel then evaluates the reference's own loop condition every step)
+  long long n_full_steps;
   size_t n_traj;
   const double* y0;
   const double* params;
@@ -146,6 +150,7 @@ struct DdeFixedStepper {
   int w;
   uint32_t status;
   bool loaded, uniform;
+  bool track_oldest;  // max_delay < tau: "deleted time range" panics (state.rs:166-171) are possible
   unsigned warp_base, slot_stride;  // ring addressing in doubles: [slot][warp][F][32] (host guarantees < 2^32)
 
   __device__ DdeFixedStepper(const DdeFixedArgs& A_, size_t g_, size_t gid_, bool valid_, double* sm_)
@@ -269,10 +274,14 @@ struct DdeFixedStepper {
   __device__ __forceinline__ void refill(int s, double tau, double h) {
     // prune rule of commit_step (state.rs:126-133) replayed on the shared time grid:
     // pop while t_deque[1] < t_prev - max_delay
-    const double t_tail = t_prev - A.max_delay;
-    while (t_old1 < t_tail && t_old1 < t_prev) {
-      t_oldest = t_old1;
-      t_old1 = t_old1 + h;
+    // (needed only when the retained window may be shorter than the delay: with max_delay >= tau
+    // no lookup can fall before the oldest retained record, see run())
+    if (track_oldest) {
+      const double t_tail = t_prev - A.max_delay;
+      while (t_old1 < t_tail && t_old1 < t_prev) {
+        t_oldest = t_old1;
+        t_old1 = t_old1 + h;
+      }
     }
     int issued_before;  // highest record issued by earlier refills
     if (!loaded) {
@@ -321,6 +330,10 @@ struct DdeFixedStepper {
     // the staged (warp-cooperative) path needs one window position per warp
     uniform = __all_sync(0xffffffffu, __double_as_longlong(tau) ==
                                           __shfl_sync(0xffffffffu, __double_as_longlong(tau), 0));
+    // The reference's prune leaves a front record older than t_prev - max_delay - h; every lookup of
+    // this system is at t - tau >= t_prev - tau.  With max_delay >= tau the front can never be
+    // newer than a lookup, so the replay of the prune (and its per-step check) is skipped.
+    track_oldest = !(A.max_delay >= tau);
     const size_t n_warps = (n_traj + 31) / 32;
     slot_stride = unsigned(n_warps * size_t(kWarpRec));
     warp_base = unsigned((g_thread / 32) * size_t(kWarpRec));
@@ -354,8 +367,10 @@ struct DdeFixedStepper {
       const double h = A.h;
       // Phase A: some lookup of the step may still reach the history function, or the
       // delay does not exceed the step: every lookup carries the reference's checks.
+      const bool counted = A.n_full_steps >= 0;
+      const int n_full = int(A.n_full_steps);
 #pragma unroll 1
-      while (t_curr < A.t1 && (A.t1 - t_curr) >= h &&
+      while ((counted ? s < n_full : (t_curr < A.t1 && (A.t1 - t_curr) >= h)) &&
              !(loaded && (t_curr - tau) > A.t0 && (t_curr - tau) >= tw0 && (t_curr + h) - tau < t_curr)) {
         step<true, false>(h);
         commit<true>(s, h);
@@ -367,8 +382,8 @@ struct DdeFixedStepper {
       // per step: the earliest delayed stage time against the oldest retained record
       // (state.rs:166-171).
 #pragma unroll 1
-      while (t_curr < A.t1 && (A.t1 - t_curr) >= h) {
-        if ((t_curr + A.hc_min) - tau < t_oldest) status |= DFB_TRAJ_HISTORY_DELETED;
+      while (counted ? s < n_full : (t_curr < A.t1 && (A.t1 - t_curr) >= h)) {
+        if (track_oldest && (t_curr + A.hc_min) - tau < t_oldest) status |= DFB_TRAJ_HISTORY_DELETED;
         step<true, true>(h);
         commit<true>(s, h);
         refill(s, tau, h);

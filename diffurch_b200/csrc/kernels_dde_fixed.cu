@@ -103,6 +103,16 @@ int run_dde_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t
     if (A.hc[i] < A.hc_min) A.hc_min = A.hc[i];
   A.history_id = history_id;
   A.ring_capacity = ring_capacity;
+  A.n_full_steps = -1;
+  if (h > 0.0 && (t1 - t0) / h < 5.0e7) {  // replay of solver.rs:292-293 on the shared time grid
+    long long cnt = 0;
+    volatile double t = t0;                 // volatile: one IEEE double addition per step, as on the device
+    while (t < t1 && (t1 - t) >= h) {
+      t = t + h;
+      ++cnt;
+    }
+    if (cnt < 2000000000LL) A.n_full_steps = cnt;
+  }
   A.n_traj = n;
   A.y0 = y0;
   A.params = params;

@@ -336,6 +336,53 @@ def test_fuzz_output_policies_and_ragged_sizes(oracle, seed):
     assert np.all(g.trace_n <= cap)
 
 
+@pytest.mark.parametrize("seed", range(16))
+def test_fuzz_fast_arithmetic_within_tolerance(oracle, seed):
+    # FAST (FMA, pre-scaled rows, pre-combined interpolants) against the STRICT oracle on non-chaotic
+    # systems: north_star's 1e-12 relative for fixed-step trajectories, event times within 1e-10
+    rng = np.random.default_rng(17000 + seed)
+    n = int(rng.integers(1, 200))
+    rk, rk_name = pick_rk(rng)
+    if rng.random() < 0.6:
+        k = rng.integers(0, 3)
+        if k == 0:
+            system, prm, y0 = d.systems.Harmonic, None, rng.uniform(-2, 2, (n, 2))
+        elif k == 1:
+            system, prm, y0 = d.systems.Linear1, rng.uniform(-2, 0.5, (n, 1)), rng.uniform(0.5, 2, (n, 1))
+        else:
+            system, prm, y0 = d.systems.Time3, None, rng.uniform(-1, 1, (n, 3))
+        h = float(rng.choice([0.1, 0.03, 1.0 / 64]))
+        t1 = float(rng.uniform(5.0, 60.0)) * h
+
+        def mk(arith):
+            s = d.Solver.new().initial(y0).interval(0.0, t1).stepsize(h).rk(rk).arith(arith)
+            return s.equation(system, prm) if prm is not None else s.equation(system)
+        g = mk("fast").run()
+        o = oracle.run_solver(mk("strict"), n_threads=4)
+        what = f"[seed {seed}: {system.name} n={n} rk={rk_name} h={h} t1={t1}]"
+        assert np.array_equal(g.steps, o.steps) and np.array_equal(g.t, o.t) and np.all(g.status == 0), what
+        assert np.max(np.abs(g.p - o.p) / np.maximum(np.abs(o.p), 1.0)) < 1e-12, what
+    else:
+        y0 = np.stack([rng.uniform(0.5, 2.0, n), rng.uniform(-1.0, 1.0, n)], 1)
+        prm = np.tile([9.8, float(rng.uniform(0.85, 0.95))], (n, 1))
+        h = float(rng.choice([0.005, 0.01, 0.02]))
+        rk43 = rng.random() < 0.3
+
+        def mk(arith):
+            s = (d.Solver.new().initial(y0).equation(d.systems.BouncingBall, prm).interval(0.0, 2.0).stepsize(h)
+                 .on(d.Locator.zero("dx"), None).on_mut(d.Locator.below_zero("x"), "bounce")
+                 .log_events(d.EventLog(64)).arith(arith).max_steps(5000))
+            return s.rk(d.RK.rk43()) if rk43 else s
+        g = mk("fast").run()
+        o = oracle.run_solver(mk("strict"), n_threads=4)
+        what = f"[seed {seed}: bouncing ball n={n} h={h} rk43={rk43}]"
+        assert g.totals["kernel_kind"] == abi.KERNEL_ODE_EVENT
+        assert np.array_equal(g.event_n, o.event_n) and np.array_equal(g.event_index, o.event_index), what
+        assert np.array_equal(g.steps, o.steps), what
+        assert np.max(np.abs(g.event_t - o.event_t)) < 1e-10, what
+        assert np.max(np.abs(g.p - o.p)) < 1e-9, what
+
+
 def test_fuzz_reached_every_ode_kernel_family():
     # runs last in this file: the random configurations above must have exercised these kernels
     if not SEEN:

@@ -17,6 +17,9 @@ from diffurch_b200 import abi
 
 pytestmark = pytest.mark.gpu
 
+# DFB_FUZZ_SCALE=k multiplies the number of seeds of every test (a longer campaign on demand)
+SCALE = max(1, int(os.environ.get("DFB_FUZZ_SCALE", "1")))
+
 RK_NAMES = ["euler", "midpoint", "heun2", "ralston2", "kutta3", "heun3", "ralston3", "wray3", "ssp3", "rk4",
             "three_eights", "rk43", "rktp64"]
 SEEN = set()
@@ -83,7 +86,7 @@ def ode_system(rng, n):
     return d.systems.Linear3Matrix, rng.uniform(-1, 1, (n, 9)), np.tile(np.eye(3).reshape(1, 9), (n, 1)), 0.0
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(24 * SCALE))
 def test_fuzz_fixed_step_ode_strict_bit_exact(oracle, seed):
     rng = np.random.default_rng(1000 + seed)
     n = int(rng.integers(1, 130))
@@ -125,7 +128,7 @@ LOCATIONS = [abi.LOCATE_STEP_BEGIN, abi.LOCATE_STEP_END, abi.LOCATE_STEP_MIDDLE,
              abi.LOCATE_BISECTION, abi.LOCATE_BISECTION_BOOL, abi.LOCATE_REGULA_FALSI]
 
 
-@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("seed", range(40 * SCALE))
 def test_fuzz_located_events_strict_bit_exact(oracle, seed):
     rng = np.random.default_rng(5000 + seed)
     n = int(rng.integers(1, 100))
@@ -204,7 +207,7 @@ def test_fuzz_located_events_strict_bit_exact(oracle, seed):
     same(g, o, what)
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(12 * SCALE))
 def test_fuzz_dde_strict_vs_oracle(oracle, seed):
     # the sin history / exact solution put sin() on both sides: compare to 1e-13, counters exactly
     rng = np.random.default_rng(9000 + seed)
@@ -233,7 +236,7 @@ def test_fuzz_dde_strict_vs_oracle(oracle, seed):
         assert np.max(np.abs(g.p - o.p)) < tol * max(1.0, float(np.max(np.abs(o.p)))), what
 
 
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", range(10 * SCALE))
 def test_fuzz_adaptive_vs_oracle(oracle, seed):
     # AutomaticStepsize: STRICT (general kernel, libm-like pow on both sides, <= 2 ulp apart) and FAST
     # (ode_adaptive_kernel, Newton root) against the oracle: same step sequence up to one step near
@@ -266,7 +269,7 @@ def test_fuzz_adaptive_vs_oracle(oracle, seed):
         assert np.max(np.abs(g.p[ok] - o.p[ok]) / scale, initial=0.0) < 100 * tol, what
 
 
-@pytest.mark.parametrize("seed", range(16))
+@pytest.mark.parametrize("seed", range(16 * SCALE))
 def test_fuzz_dde_events_and_propagation_strict_bit_exact(oracle, seed):
     # delay systems without transcendental calls, through the general kernel: the relay-clamp DDE
     # (examples/dde-relay-clamp.rs) and y' = 0 with propagated discontinuities
@@ -316,7 +319,7 @@ def test_fuzz_dde_events_and_propagation_strict_bit_exact(oracle, seed):
     same(g, o, what)
 
 
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", range(10 * SCALE))
 def test_fuzz_output_policies_and_ragged_sizes(oracle, seed):
     # traces with `every` > 1 and a capacity smaller than the number of samples, event logs that
     # overflow their capacity (the count keeps running), member counts around the warp / block edges
@@ -336,7 +339,7 @@ def test_fuzz_output_policies_and_ragged_sizes(oracle, seed):
     assert np.all(g.trace_n <= cap)
 
 
-@pytest.mark.parametrize("seed", range(16))
+@pytest.mark.parametrize("seed", range(16 * SCALE))
 def test_fuzz_fast_arithmetic_within_tolerance(oracle, seed):
     # FAST (FMA, pre-scaled rows, pre-combined interpolants) against the STRICT oracle on non-chaotic
     # systems: north_star's 1e-12 relative for fixed-step trajectories, event times within 1e-10

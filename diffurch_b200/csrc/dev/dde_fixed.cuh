@@ -41,6 +41,7 @@ struct DdeFixedArgs {
   double t0, t1, h;
   double max_delay;       // Solver::max_delay: the retained history window (state.rs:126-133)
   double hc_min;          // min over stages i >= 1 of c_i * h (earliest delayed stage time of a step)
+  double c_min;           // the same stage's c_i (for steps shorter than h)
   int32_t history_id;
   int32_t ring_capacity;  // power of two
   // full steps of length h that Solver::run takes before the closing partial step (solver.rs:292-293),
@@ -294,7 +295,14 @@ struct DdeFixedStepper {
     } else {
       issued_before = (w + 2 < s - 1) ? w + 2 : s - 1;
     }
-    const double tt_min = t_curr - tau;  // earliest delayed time of the next step (c_0 = 0)
+    // Earliest lookup of the NEXT step: stage 0 reuses d_curr (no lookup), so it is the stage with
+    // the smallest c_i > 0, evaluated with the very expression that stage will use.  Sliding on it
+    // (not on t_curr - tau) puts every lookup of the step in [T_w, T_w+2): they span less than
+    // (1 - c_min) h.  Sliding on t_curr - tau let the end-of-step lookup reach T_w+2 by one ulp when
+    // tau / h is an integer, and the window then extrapolated record w+1 where the reference reads
+    // record w+2 — invisible for a smooth interpolant, an O(h) error for y'(t - tau) of a linear one.
+    const double next_len = fmin(h, A.t1 - t_curr);
+    const double tt_min = (t_curr + (next_len == h ? A.hc_min : A.c_min * next_len)) - tau;
     while (tw1 <= tt_min) {              // record w+1 starts at or before it: slide
       ++w;
       tw0 = tw1;
@@ -371,7 +379,8 @@ struct DdeFixedStepper {
       const int n_full = int(A.n_full_steps);
 #pragma unroll 1
       while ((counted ? s < n_full : (t_curr < A.t1 && (A.t1 - t_curr) >= h)) &&
-             !(loaded && (t_curr - tau) > A.t0 && (t_curr - tau) >= tw0 && (t_curr + h) - tau < t_curr)) {
+             !(loaded && (t_curr + A.hc_min) - tau > A.t0 && (t_curr + A.hc_min) - tau >= tw0 &&
+               (t_curr + h) - tau < t_curr)) {
         step<true, false>(h);
         commit<true>(s, h);
         refill(s, tau, h);

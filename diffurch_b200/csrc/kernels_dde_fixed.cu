@@ -99,8 +99,13 @@ int run_dde_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t
   A.h = h;
   A.max_delay = max_delay;
   A.hc_min = A.hc[rk.S > 1 ? 1 : 0];
+  A.c_min = A.c[rk.S > 1 ? 1 : 0];
   for (int i = 1; i < rk.S; ++i)
-    if (A.hc[i] < A.hc_min) A.hc_min = A.hc[i];
+    if (A.hc[i] < A.hc_min) {
+      A.hc_min = A.hc[i];
+      A.c_min = A.c[i];
+    }
+  if (!(A.c_min > 0.0)) return -1;  // a stage at the step start would look up t_prev - tau: general kernel
   A.history_id = history_id;
   A.ring_capacity = ring_capacity;
   A.n_full_steps = -1;

@@ -450,6 +450,27 @@ def test_dde_hot_path_other_tableaux_and_delays(oracle):
             assert np.max(np.abs(g.p - o.p) / np.maximum(np.abs(o.p), 1.0)) < 1e-12, (rk, tau / h)
 
 
+
+def test_dde_hot_path_delay_is_an_exact_multiple_of_the_step(oracle):
+    # tau / h an integer puts every delayed stage time one ulp away from a record boundary.  The
+    # reference then reads the record that STARTS at the boundary; for y'(t - tau) of a linear
+    # interpolant (rk4) the neighbouring record's value differs by O(h).  Found by the fuzz campaign
+    # (tests/test_fuzz_parity.py, seed 54 at DFB_FUZZ_SCALE=6): the window used to slide on
+    # t - tau instead of the earliest lookup of the step.
+    k = 0.4 + np.arange(64) / 63.0
+    for tau, h, rk in ((0.5, 0.05, d.RK.rk4()), (1.0, 0.125, d.RK.rk4()), (0.5, 0.025, d.RK.rk43()),
+                       (1.0, 0.02, d.RK.rktp64())):
+        for system, prm, init in ((d.systems.NddeLinear, cases.ndde_params(k, tau), d.InitFn(d.SIN, d.SIN_DERIV)),
+                                  (d.systems.DdeLinear, cases.dde_params(k, tau), d.InitFn(d.SIN))):
+            mk = lambda arith: (d.Solver.new().max_delay(tau).initial(init).interval(0.0, 4.0).stepsize(h).rk(rk)
+                                .equation(system, prm).arith(arith))
+            f = mk("fast").run()
+            assert f.totals["kernel_kind"] == d.abi.KERNEL_DDE_FIXED and np.all(f.status == 0)
+            o = oracle.run_solver(mk("strict"), n_threads=4)
+            assert np.array_equal(f.steps, o.steps) and np.array_equal(f.t, o.t)
+            assert np.max(np.abs(f.p - o.p)) < 1e-11, (system.name, tau, h)
+
+
 def test_dde_hot_path_panics_become_status_bits(oracle):
     mk = lambda: cases.eq_dde_sin(trace=False, arith="fast").stepsize(1.5)   # delay <= h
     g, o = mk().run(), oracle.run_solver(mk())

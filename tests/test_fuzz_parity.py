@@ -215,13 +215,16 @@ def test_fuzz_dde_strict_vs_oracle(oracle, seed):
     k = rng.uniform(0.4, 1.4, n)
     tau = float(rng.choice([1.0, 0.5, 0.73]))
     h = float(rng.choice([0.02, 0.05, 0.011]))
+    per_member = rng.random() < 0.3      # a different delay per member: the lanes of a warp disagree on the window
+    taus = rng.choice([1.0, 0.5, 0.73, 0.25], size=n) if per_member else np.full(n, tau)
+    tau = float(np.max(taus))
     rk, rk_name = [(d.RK.rktp64(), "rktp64"), (d.RK.rk43(), "rk43"), (d.RK.rk4(), "rk4")][rng.integers(0, 3)]
     neutral = rng.random() < 0.4
     import cases
     if neutral:
-        prm, system, init = cases.ndde_params(k, tau), d.systems.NddeLinear, d.InitFn(d.SIN, d.SIN_DERIV)
+        prm, system, init = cases.ndde_params(k, taus), d.systems.NddeLinear, d.InitFn(d.SIN, d.SIN_DERIV)
     else:
-        prm, system, init = cases.dde_params(k, tau), d.systems.DdeLinear, d.InitFn(d.SIN)
+        prm, system, init = cases.dde_params(k, taus), d.systems.DdeLinear, d.InitFn(d.SIN)
     t1 = float(rng.uniform(1.0, 6.0))
     for arith, tol in (("strict", 1e-13), ("fast", 1e-11)):
         def mk():
@@ -230,7 +233,7 @@ def test_fuzz_dde_strict_vs_oracle(oracle, seed):
         g = mk().run()
         o = oracle.run_solver(mk(), n_threads=4)
         SEEN.add(g.totals["kernel_kind"])
-        what = f"[seed {seed}: {system.name} n={n} tau={tau} h={h} rk={rk_name} t1={t1} {arith}]"
+        what = f"[seed {seed}: {system.name} n={n} tau={tau} per_member={per_member} h={h} rk={rk_name} t1={t1} {arith}]"
         assert np.array_equal(g.steps, o.steps) and np.array_equal(g.status, o.status), what
         assert np.array_equal(g.t, o.t), what
         assert np.max(np.abs(g.p - o.p)) < tol * max(1.0, float(np.max(np.abs(o.p)))), what

@@ -335,6 +335,8 @@ struct DiscoList {
 };
 
 enum : int { MODE_STEP = 0, MODE_EVENT_RESTEP = 1, MODE_LOCATE = 2, MODE_DONE = 3 };
+// status bits that stand for a `panic!` of the reference: the trajectory ends where it was raised
+constexpr uint32_t kPanicBits = DFB_TRAJ_HISTORY_DELETED | DFB_TRAJ_HISTORY_NOT_READY | DFB_TRAJ_NO_DERIVATIVE;
 
 // ODEHIST: keep the delay-history ring for a system that never looks anything up itself.  The
 // reference stores the last two steps even for ODEs (commit_step with max_delay = 0 keeps three
@@ -814,7 +816,9 @@ struct Integrator {
               }
             }
           }
-          if (found && best_t >= t_prev) {  // solver.rs:299-300
+          if (hist.status & kPanicBits) {
+            mode = MODE_DONE;  // a lookup inside a locator panicked upstream: the step is never committed
+          } else if (found && best_t >= t_prev) {  // solver.rs:299-300
             undo_step();
             ev_time = best_t;
             ev_index = best_i;
@@ -837,8 +841,7 @@ struct Integrator {
         double h_before = 0.0;
         const double h_req = restep ? (ev_time - t_curr) : fmin(stepsize_get(), P.t1 - t_curr);
         make_step(h_req, adaptive);
-        if (hist.status & (DFB_TRAJ_HISTORY_DELETED | DFB_TRAJ_HISTORY_NOT_READY |
-                           DFB_TRAJ_NO_DERIVATIVE)) {
+        if (hist.status & kPanicBits) {
           mode = MODE_DONE;  // the reference panics here
         } else if (HAS_LOC && restep) {
           // solver.rs:304-309
@@ -875,7 +878,9 @@ struct Integrator {
             for (int l = 0; l < P.n_loc; ++l)
               if (detect_phase(l)) fired_mask |= 1u << l;
           }
-          if (fired_mask != 0u) {
+          if (hist.status & kPanicBits) {
+            mode = MODE_DONE;  // a detector (or a FilterLocated locate) looked up a time the reference panics on
+          } else if (fired_mask != 0u) {
             mode = MODE_LOCATE;
           } else {
             commit_step();

@@ -105,8 +105,11 @@ def test_fuzz_fixed_step_ode_strict_bit_exact(oracle, seed):
         if periodic:
             cb = "renormalize" if system is d.systems.Linear1 else "qr_ln_abs"
             s = s.on_mut(d.Periodic(float(rng_period), float(rng_offset)), cb)
+            if two_periodics:   # coinciding times: earliest wins, lowest index on ties, DedupLocF per locator
+                s = s.on_mut(d.Periodic(float(rng_period) * 1.5, 0.0), cb)
         return s
     rng_period, rng_offset = rng.uniform(2.0, 9.0) * h, rng.uniform(0.0, 1.0) * h
+    two_periodics = rng.random() < 0.5
     what = f"[seed {seed}: {system.name} n={n} rk={rk_name} h={h} t=[{t0},{t1}] trace={trace is not None} periodic={periodic}]"
     g = mk().run()
     o = oracle.run_solver(mk(), n_threads=4)

@@ -123,7 +123,7 @@ class Problem(C.Structure):
         ("h", C.c_double),
         ("automatic", AutoStepsize),
         ("max_delay", C.c_double),
-        ("n_disco", C.c_int32), ("_pad0", C.c_int32),
+        ("n_disco", C.c_int32), ("on_start_callback_id", C.c_int32),
         ("disco_t", C.c_double * MAX_DISCO),
         ("disco_order", C.c_int32 * MAX_DISCO),
         ("loc", Locator * MAX_LOCATORS),

@@ -277,6 +277,8 @@ int validate(const dfb_problem& p, const SysInfo** info_out) {
           return fail(DFB_ERR_INVALID, "on_times: indices must be non-negative and strictly increasing");
     }
   }
+  if (p.on_start_callback_id < 0 || p.on_start_callback_id > info->n_callbacks)
+    return fail(DFB_ERR_INVALID, "on_start_callback_id not registered for this system");
   if (p.trace_every < 0 || p.trace_capacity < 0 || p.event_capacity < 0 || p.ring_capacity < 0)
     return fail(DFB_ERR_INVALID, "negative capacity");
   *info_out = info;
@@ -482,6 +484,7 @@ int dfb_create(const dfb_problem* desc, size_t n_traj, int device, dfb_handle** 
     const int S_ = desc->rk.S, I_ = desc->rk.I;
     const bool shape_ok = (S_ == 7 && I_ == 5) || (S_ == 5 && I_ == 4) || (S_ == 4 && I_ == 2);
     h->dde_hot = info->uses_history && desc->arith == DFB_ARITH_FAST &&
+                 desc->on_start_callback_id == DFB_CB_NONE &&
                  desc->stepsize_kind == DFB_STEP_FIXED && desc->n_loc == 0 && desc->n_disco == 0 &&
                  desc->trace_every == 0 && desc->max_steps == 0 && shape_ok &&
                  dde_hot_system(desc->system_id) && table_for(desc->system_id, DFB_ARITH_FAST).dde_fixed &&
@@ -599,7 +602,8 @@ int dfb_run(dfb_handle* h, void* stream_v) {
   const DfbLaunchTable& T = table_for(p.system_id, p.arith);
 
   // Hot path: fixed step, no locators, no history, final state only.
-  const bool hot_eligible = p.stepsize_kind == DFB_STEP_FIXED && p.n_loc == 0 &&
+  const bool no_start_cb = p.on_start_callback_id == DFB_CB_NONE;
+  const bool hot_eligible = no_start_cb && p.stepsize_kind == DFB_STEP_FIXED && p.n_loc == 0 &&
                             !h->info.uses_history && p.trace_every == 0 && p.max_steps == 0 &&
                             p.history_id == DFB_HIST_CONSTANT && !std::getenv("DFB_FORCE_GENERAL");
   h->kernel_kind = DFB_KERNEL_GENERAL;
@@ -624,7 +628,7 @@ int dfb_run(dfb_handle* h, void* stream_v) {
 
   // Fixed step + Periodic callbacks (dev/ode_fixed.cuh, OdeFixedPeriodicStepper): the Lyapunov-batch
   // shape.  Every locator must be an unfiltered Periodic; final state / aux / event log only.
-  bool periodic_eligible = p.stepsize_kind == DFB_STEP_FIXED && p.n_loc > 0 && !h->info.uses_history &&
+  bool periodic_eligible = no_start_cb && p.stepsize_kind == DFB_STEP_FIXED && p.n_loc > 0 && !h->info.uses_history &&
                            p.trace_every == 0 && p.max_steps == 0 && p.history_id == DFB_HIST_CONSTANT &&
                            !std::getenv("DFB_FORCE_GENERAL");
   for (int l = 0; l < p.n_loc && periodic_eligible; ++l)
@@ -662,7 +666,7 @@ int dfb_run(dfb_handle* h, void* stream_v) {
                         p.n_loc, p.loc, p.event_capacity, h->d_ev_t, h->d_ev_idx, h->d_nevents,
                         tracing ? p.trace_every : 0, p.trace_capacity, tracing ? h->d_trace_t : nullptr,
                         h->d_trace_y, h->d_nsamples, h->d_queue, h->locate_batch, h->locate_max_wait, h->n_sm,
-                        stream);
+                        p.on_start_callback_id, stream);
     if (rc > 0) return fail(DFB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(cudaError_t(rc)));
     if (rc == 0) {
       DFB_CUDA(cudaEventRecord(h->ev1, stream));
@@ -675,7 +679,7 @@ int dfb_run(dfb_handle* h, void* stream_v) {
 
   // Adaptive hot path (dev/ode_adaptive.cuh): AutomaticStepsize, no locators, no history,
   // final state only, FAST arithmetic.
-  const bool adaptive_eligible = p.stepsize_kind == DFB_STEP_AUTOMATIC && p.n_loc == 0 &&
+  const bool adaptive_eligible = no_start_cb && p.stepsize_kind == DFB_STEP_AUTOMATIC && p.n_loc == 0 &&
                                  !h->info.uses_history && p.trace_every == 0 && p.max_steps == 0 &&
                                  p.history_id == DFB_HIST_CONSTANT && p.arith == DFB_ARITH_FAST &&
                                  !std::getenv("DFB_FORCE_GENERAL");
@@ -737,6 +741,7 @@ int dfb_run(dfb_handle* h, void* stream_v) {
   P.ring_capacity = h->ring_capacity;
   P.uses_disco = h->uses_disco ? 1 : 0;
   P.ode_history = h->ode_history ? 1 : 0;
+  P.on_start_cb = p.on_start_callback_id;
   // pre-combined history records need b_i(0) = 0 for every stage (true of every rk.rs tableau)
   P.coeff_records = (p.arith == DFB_ARITH_FAST && h->info.uses_history && !std::getenv("DFB_NO_COEFF_RECORDS")) ? 1 : 0;
   for (int i = 0; i < p.rk.S && P.coeff_records; ++i)

@@ -40,7 +40,7 @@ struct DevProblem {
   int32_t uses_disco;  // any PROPAGATION locator or initial_disco entry
   int32_t coeff_records;  // FAST: history records hold pre-combined interpolant coefficients (integrator.cuh)
   int32_t ode_history;    // an ODE problem whose locators may evaluate the state outside the step in flight
-  int32_t _pad1;
+  int32_t on_start_cb;    // Solver::on_start_mut: callback id run on the initial State (0 = none)
   long long max_steps;
   size_t n_traj;
   // inputs (SoA, trajectory index fastest)

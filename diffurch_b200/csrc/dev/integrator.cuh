@@ -737,6 +737,10 @@ struct Integrator {
     n_steps = n_rejected = n_events = n_rhs = 0ull;
     n_samples = n_evlog = 0u;
     on_step_calls = 0ull;
+    if (P.on_start_cb != DFB_CB_NONE) {  // events_on_start.eval_mut (solver.rs:289), before the first on_step
+      RefMut m{&t_curr, p_curr, d_curr, t_prev, p_prev, &hist};
+      Sys::callback(P.on_start_cb, m, prm, aux);
+    }
   }
 
   __device__ void finish() {

@@ -314,6 +314,10 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
     }
     n_steps = n_events = n_evlog = n_samples = 0u;
     n_rhs = on_step_calls = 0ull;
+    if (A.on_start_cb != DFB_CB_NONE) {  // events_on_start.eval_mut (solver.rs:289)
+      RefMut m{&t_curr, p_curr(), d_curr(), t_prev, p_prev(), &this->nohist};
+      Sys::callback(A.on_start_cb, m, prm(), aux);
+    }
     on_step();  // events_on_step at t_init (solver.rs:290)
     return next_mode();
   }

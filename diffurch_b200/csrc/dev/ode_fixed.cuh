@@ -54,6 +54,7 @@ struct OdeFixedArgs {
   unsigned long long* queue;     // work counter (zeroed before the launch)
   int32_t locate_batch, locate_wait;
   int32_t inner_steps;           // step rounds between two warp votes (>= 1)
+  int32_t on_start_cb;           // Solver::on_start_mut: callback id run on the initial State (0 = none)
   int32_t trace_every, trace_capacity;
   double* trace_t;               // [cap][n]
   double* trace_y;               // [cap][N][n]

@@ -200,6 +200,9 @@ class Solver {
   }
   Solver& on(Loc loc, int callback_id = DFB_CB_NONE) { return append(loc, callback_id, 1); }      // solver.rs:199
   Solver& on_mut(Loc loc, int callback_id) { return append(loc, callback_id, 1); }                // solver.rs:219
+  Solver& on_start_mut(int callback_id) { p_.on_start_callback_id = callback_id; return *this; }   // solver.rs:190
+  Solver& on_start() { return *this; }  // solver.rs:181: read-only, observes the initial state the caller holds
+  Solver& on_stop() { return *this; }   // solver.rs:172: read-only, observes the final State run() returns
   Solver& with_delayed_argument(int delayed_id, int smoothing_order) {                            // solver.rs:239
     Loc l;
     l.l.kind = DFB_LOC_PROPAGATION;

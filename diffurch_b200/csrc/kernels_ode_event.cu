@@ -73,7 +73,7 @@ int run_ode_event_shim(int system_id, const dfb_tableau& rk, double t0, double t
                        int event_capacity, double* ev_t, int32_t* ev_idx, uint32_t* n_events, int trace_every,
                        int trace_capacity, double* trace_t, double* trace_y, uint32_t* n_samples,
                        unsigned long long* queue, int locate_batch, int locate_wait, int n_sm,
-                       cudaStream_t stream) {
+                       int on_start_cb, cudaStream_t stream) {
   OdeFixedArgs A;
   std::memset(&A, 0, sizeof(A));
   for (int i = 0; i < DFB_MAX_STAGES; ++i) {
@@ -114,6 +114,7 @@ int run_ode_event_shim(int system_id, const dfb_tableau& rk, double t0, double t
   A.queue = queue;
   A.locate_batch = locate_batch;
   A.locate_wait = locate_wait;
+  A.on_start_cb = on_start_cb;
   A.inner_steps = 4;
   if (const char* e = std::getenv("DFB_EVENT_INNER")) A.inner_steps = std::atoi(e) > 0 ? std::atoi(e) : 1;
   return launch_ode_event(system_id, rk.S, rk.I, A, n_sm, stream);

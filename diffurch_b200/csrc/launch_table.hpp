@@ -23,7 +23,7 @@ typedef int (*DfbOdeEventFn)(int system_id, const dfb_tableau& rk, double t0, do
                              int n_loc, const dfb_locator* loc, int event_capacity, double* ev_t,
                              int32_t* ev_idx, uint32_t* n_events, int trace_every, int trace_capacity,
                              double* trace_t, double* trace_y, uint32_t* n_samples, unsigned long long* queue,
-                             int locate_batch, int locate_wait, int n_sm, cudaStream_t stream);
+                             int locate_batch, int locate_wait, int n_sm, int on_start_cb, cudaStream_t stream);
 typedef int (*DfbOdeAdaptiveFn)(int system_id, const dfb_tableau& rk, const dfb_auto_stepsize& ctl, double t0,
                                 double t1, size_t n, const double* y0, const double* params, double* t_final,
                                 double* y_final, unsigned long long* steps, unsigned long long* rejected,
@@ -65,12 +65,12 @@ struct DfbLaunchTable {
                          const double*, const double*, double*, double*, double*,                   \
                          unsigned long long*, unsigned long long*, unsigned long long*, uint32_t*,  \
                          int, const dfb_locator*, int, double*, int32_t*, uint32_t*, int, int,      \
-                         double*, double*, uint32_t*, unsigned long long*, int, int, int,           \
+                         double*, double*, uint32_t*, unsigned long long*, int, int, int, int,      \
                          cudaStream_t);                                                              \
   }
 
 // What a plugin's `dfb_plugin_describe` fills in (csrc/plugin_entry.cu).
-#define DFB_PLUGIN_ABI 2
+#define DFB_PLUGIN_ABI 3
 struct dfb_plugin_desc {
   int plugin_abi;
   int n_state, n_params, n_aux, n_detectors, n_callbacks, uses_history;

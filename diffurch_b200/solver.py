@@ -277,6 +277,26 @@ class Solver:
         self._problem.trace_capacity = policy.capacity
         return self
 
+    def on_start_mut(self, callback):
+        """``Solver::on_start_mut`` (solver.rs:190-197): a registered mutating callback run once on
+        the initial State, before the first ``on_step``."""
+        if self._system is None:
+            raise ValueError("call .equation(system, params) before registering callbacks")
+        cb = self._system.callbacks[callback] if isinstance(callback, str) else int(callback or 0)
+        self._problem.on_start_callback_id = cb
+        return self
+
+    def on_start(self, callback=None):
+        """``Solver::on_start`` (solver.rs:181-188) takes a read-only closure: it observes the
+        initial state, which the caller of a batched solve already holds.  Accepted for source
+        compatibility; nothing is sent to the device."""
+        return self
+
+    def on_stop(self, callback=None):
+        """``Solver::on_stop`` (solver.rs:172-179), read-only: it observes the final State, which
+        ``run()`` returns.  Accepted for source compatibility."""
+        return self
+
     def log_events(self, policy):
         self._problem.event_capacity = policy.capacity
         return self

@@ -262,7 +262,11 @@ typedef struct dfb_problem {
   dfb_auto_stepsize automatic;
   double max_delay;     /*                        <- Solver::max_delay (solver.rs:130) */
   int32_t n_disco;      /*                        <- Solver::initial_disco (solver.rs:114) */
-  int32_t _pad0;
+  int32_t on_start_callback_id; /*               <- Solver::on_start_mut (solver.rs:190-197): system-local
+                                   callback id run once on the initial State, before the first
+                                   on_step; DFB_CB_NONE = none.  (Read-only on_start / on_stop closures,
+                                   solver.rs:172-188, observe what the caller already holds: the initial
+                                   state and the final State that dfb_get_final returns.) */
   double disco_t[DFB_MAX_DISCO];
   int32_t disco_order[DFB_MAX_DISCO];
   dfb_locator loc[DFB_MAX_LOCATORS];

@@ -778,6 +778,7 @@ struct Solver {
   Stepsize<N> stepsize;
   double max_delay = 0.0;
   std::vector<std::function<void(const Ref&)>> events_on_step, events_on_start, events_on_stop;
+  std::function<void(StateRefMut<N, S, I>&)> on_start_mut;
   std::vector<std::unique_ptr<LocBase<N, S, I>>> events_on_loc;
   uint64_t max_steps = 0;  // oracle-only guard for unbounded intervals
 
@@ -835,6 +836,10 @@ struct Solver {
     St state(t_init, max_delay, initial, initial_disco, rk);
     auto& rhs = equation;
     fire(events_on_start, state);
+    if (on_start_mut) {  // a `new_mut` element of events_on_start (solver.rs:190-197)
+      StateRefMut<N, S, I> m{state.t_curr, state.p_curr, state.d_curr, state.t_prev, state.p_prev, state.history};
+      on_start_mut(m);
+    }
     fire(events_on_step, state);
     while (state.t_curr < t_end) {
       state.make_step(rhs, std::fmin(stepsize.get(), t_end - state.t_curr));

@@ -236,6 +236,7 @@ void run_one(const RunArgs& A, size_t i) {
     });
   }
   solver.log_events = A.ev_t != nullptr && d.event_capacity > 0;
+  if (d.on_start_callback_id != DFB_CB_NONE) solver.on_start_mut = Sys::callback(d.on_start_callback_id, prm, aux);
 
   uint32_t status = TRAJ_OK;
   double t_fin = std::numeric_limits<double>::quiet_NaN();

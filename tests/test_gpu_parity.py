@@ -926,3 +926,33 @@ def test_full_size_lyapunov_batch_properties():
     assert np.max(np.abs(lam.sum(axis=1) + (10.0 + 1.0 + 8.0 / 3.0))) < 1e-6
     assert np.all(g.events == 100) and np.all(g.steps == g.steps[0])
     assert np.mean(lam[:, 0] > 0.3) > 0.9
+
+
+def test_on_start_mut_runs_once_before_the_first_on_step(oracle):
+    # Solver::on_start_mut (solver.rs:190-197, run at solver.rs:289): the registered callback mutates
+    # the initial State; the first trace sample (on_step at t_init, solver.rs:290) already sees it
+    lam = np.linspace(-1.0, 1.0, 37).reshape(-1, 1)
+    y0 = np.linspace(0.5, 4.0, 37).reshape(-1, 1)
+    for extra in ("none", "periodic", "statefn"):
+        def mk():
+            s = (d.Solver.new().initial(y0).equation(d.systems.Linear1, lam).interval(0.0, 2.0).stepsize(0.05)
+                 .on_start_mut("renormalize").on_step(d.Trace(1, 64)))
+            if extra == "periodic":
+                s = s.on_mut(d.Periodic(0.3, 0.0), "renormalize")
+            if extra == "statefn":
+                s = s.on(d.Locator.step().every(7), None)
+            return s
+        g = mk().run()
+        o = oracle.run_solver(mk(), n_threads=2)
+        assert np.all(g.trace_p[:, 0, 0] == 1.0)                       # |y0| / |y0|
+        assert_same_counters(g, o)
+        assert_same_trace(g, o, exact=True)
+        assert np.array_equal(g.p, o.p) and np.max(np.abs(g.aux - o.aux)) < 1e-13
+        assert np.all(np.abs(g.aux[:, 0] - np.log(y0[:, 0])) < 1e-12) or extra == "periodic"
+    # the register-only hot paths do not take callbacks: an on_start_mut problem goes to a kernel that does
+    plain = (d.Solver.new().initial(y0).equation(d.systems.Linear1, lam).interval(0.0, 2.0).stepsize(0.05)
+             .on_start_mut("renormalize").arith("fast").run())
+    assert plain.totals["kernel_kind"] == KERNEL_GENERAL
+    ref = (d.Solver.new().initial(np.ones_like(y0)).equation(d.systems.Linear1, lam).interval(0.0, 2.0)
+           .stepsize(0.05).arith("fast").run())
+    assert np.max(np.abs(plain.p - ref.p)) < 1e-14 and np.all(np.abs(plain.aux[:, 0] - np.log(y0[:, 0])) < 1e-12)

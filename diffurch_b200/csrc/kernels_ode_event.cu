@@ -26,6 +26,26 @@ bool try_launch(int S_rt, int I_rt, const OdeFixedArgs& A, int n_sm, cudaStream_
   if (S_rt != S || I_rt != I) return false;
   constexpr unsigned long long AM = amask_full_lower(S);
   constexpr unsigned BM = (1u << S) - 1u;
+  // every locator a plain Locator::{zero, above_zero, below_zero}: the SIMPLE profile (S = 7 only, to
+  // bound the number of instantiations)
+  bool simple = S == 7 && A.n_loc <= 2 && !getenv("DFB_EVENT_GENERIC_PROFILE");
+  for (int l = 0; l < A.n_loc && simple; ++l) {
+    const dfb_locator& L = A.loc[l];
+    simple = L.kind == DFB_LOC_STATEFN && L.location == DFB_LOCATE_BISECTION && L.filter == DFB_FILTER_NONE &&
+             (L.detection == DFB_DET_ZERO || L.detection == DFB_DET_ABOVE_ZERO || L.detection == DFB_DET_BELOW_ZERO);
+  }
+  if constexpr (S == 7) {
+    if (simple && A.n_loc <= 1) {
+      launch_grid(ode_event_kernel<Sys, S, I, AM, BM, kFast, 1, kBlock, true>, A, n_sm, stream);
+      *rc = int(cudaGetLastError());
+      return true;
+    }
+    if (simple && A.n_loc == 2) {
+      launch_grid(ode_event_kernel<Sys, S, I, AM, BM, kFast, 2, kBlock, true>, A, n_sm, stream);
+      *rc = int(cudaGetLastError());
+      return true;
+    }
+  }
   if (A.n_loc <= 1) launch_grid(ode_event_kernel<Sys, S, I, AM, BM, kFast, 1, kBlock>, A, n_sm, stream);
   else if (A.n_loc == 2) launch_grid(ode_event_kernel<Sys, S, I, AM, BM, kFast, 2, kBlock>, A, n_sm, stream);
   else launch_grid(ode_event_kernel<Sys, S, I, AM, BM, kFast, DFB_MAX_LOCATORS, kBlock>, A, n_sm, stream);

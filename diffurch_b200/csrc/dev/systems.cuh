@@ -342,7 +342,12 @@ struct SysEggBilliard : SysBase {  // examples/egg-billiard.rs:12-40
   __device__ static double detector(int, const V& s, const double*) {
     const double x = s.p[0], y = s.p[1];
     // powi(2) = y*y, powi(3) = y*(y*y)
+#if DFB_ARITH == 1
+    // FAST: the division by the constant 3 (evaluated ~45 times per located event) as a multiply
+    return x * x + y * y - (y * (y * y)) * (1.0 / 3.0) - 1.0;
+#else
     return x * x + y * y - (y * (y * y)) / 3.0 - 1.0;
+#endif
   }
   template <class M>
   __device__ static void callback(int id, M& s, const double* prm, double* aux) {

@@ -768,11 +768,10 @@ struct Integrator {
   }
 
   __device__ __forceinline__ int next_mode() {
-    if (P.max_steps > 0 && n_steps >= (unsigned long long)P.max_steps && t_curr < P.t1) {
-      hist.status |= DFB_TRAJ_STEP_LIMIT;
-      return MODE_DONE;
-    }
-    return (t_curr < P.t1) ? MODE_STEP : MODE_DONE;
+    const bool more = t_curr < P.t1;  // branch-free (see ode_event.cuh)
+    const bool limit = more && P.max_steps > 0 && n_steps >= (unsigned long long)P.max_steps;
+    hist.status |= limit ? uint32_t(DFB_TRAJ_STEP_LIMIT) : 0u;
+    return (more && !limit) ? MODE_STEP : MODE_DONE;
   }
 
   // ---- Solver::run (solver.rs:275-313) as a warp-friendly state machine -----

@@ -308,11 +308,12 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
   }
 
   __device__ __forceinline__ int next_mode() {
-    if (A.max_steps > 0 && (long long)n_steps >= A.max_steps && t_curr < A.t1) {
-      status |= DFB_TRAJ_STEP_LIMIT;
-      return MODE_DONE;
-    }
-    return (t_curr < A.t1) ? MODE_STEP : MODE_DONE;
+    // branch-free: two return paths made the compiler duplicate the (predicated) register copies
+    // that follow each call site
+    const bool more = t_curr < A.t1;
+    const bool limit = more && A.max_steps > 0 && (long long)n_steps >= A.max_steps;
+    status |= limit ? uint32_t(DFB_TRAJ_STEP_LIMIT) : 0u;
+    return (more && !limit) ? MODE_STEP : MODE_DONE;
   }
 
   // pull the next member; returns MODE_DONE when the ensemble is exhausted

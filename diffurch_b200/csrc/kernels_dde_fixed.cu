@@ -1,7 +1,7 @@
 // Instantiations + launcher of the constant-delay DDE hot-path kernel (FAST
 // arithmetic only; STRICT goes through the general integrator, which keeps the
 // reference's record format and operation order).
-#include "dev/dde_fixed.cuh"
+#include "dev/dde_fixed2.cuh"
 
 #include <cmath>
 #include <cstring>
@@ -9,6 +9,10 @@
 namespace DFB_NS {
 namespace {
 constexpr int kBlock = 128;
+#ifndef DFB_DDE_MINB2
+#define DFB_DDE_MINB2 4
+#endif
+constexpr int kMinBlocks2 = DFB_DDE_MINB2;  // two members per thread: <= 128 registers at 4 blocks/SM
 constexpr int kMinBlocks = 7;  // 7 x 128 threads: <= 72 registers; 2^18 members = 1.98 full waves on 148 SMs
 
 constexpr unsigned long long bit8(int i, int j) { return 1ull << (i * 8 + j); }
@@ -35,11 +39,22 @@ bool try_launch(int S_rt, int I_rt, unsigned long long am, unsigned bm, unsigned
                 const DdeFixedArgs& A, cudaStream_t stream, int* rc) {
   if (S_rt != S || I_rt != I) return false;
   if ((am & ~AMASK) || (bm & ~BMASK) || (bim & ~BIMASK)) return false;
-  const size_t grid = (A.n_traj + kBlock - 1) / kBlock;
-  auto kernel = dde_fixed_kernel<Sys, S, I, AMASK, BMASK, BIMASK, kBlock, kMinBlocks>;
-  // the staging buffers of kMinBlocks resident blocks need the large shared-memory carveout
-  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  kernel<<<unsigned(grid), kBlock, 0, stream>>>(A);
+  // two members per thread (dev/dde_fixed2.cuh) once the ensemble fills the device that way;
+  // DFB_DDE_TPT=1|2 overrides (tuning / tests)
+  int tpt = A.n_traj >= 65536 ? 2 : 1;
+  if (const char* e = getenv("DFB_DDE_TPT")) tpt = atoi(e) == 2 ? 2 : 1;
+  if (tpt == 2) {
+    const size_t grid = (A.n_traj + size_t(kBlock) * 2 - 1) / (size_t(kBlock) * 2);
+    auto kernel = dde_fixed2_kernel<Sys, S, I, AMASK, BMASK, BIMASK, kBlock, kMinBlocks2>;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    kernel<<<unsigned(grid), kBlock, 0, stream>>>(A);
+  } else {
+    const size_t grid = (A.n_traj + kBlock - 1) / kBlock;
+    auto kernel = dde_fixed_kernel<Sys, S, I, AMASK, BMASK, BIMASK, kBlock, kMinBlocks>;
+    // the staging buffers of kMinBlocks resident blocks need the large shared-memory carveout
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    kernel<<<unsigned(grid), kBlock, 0, stream>>>(A);
+  }
   *rc = int(cudaGetLastError());
   return true;
 }

@@ -119,7 +119,7 @@ def cpu_oracle_rate(n_sample, threads):
 
 
 DDE_MEMBERS = 1 << 18
-DDE_DRAM_TRAFFIC_PER_LAUNCH = 50286465000 + 51519552000  # ncu, profiles/r1_run9_ncu_full_dde_fixed_v5.txt
+DDE_DRAM_TRAFFIC_PER_LAUNCH = 51124647000 + 52019964000  # ncu, profiles/r1_final_ncu_full_dde_fixed.txt
 # Algorithmic bytes per RK step: one coefficient record (y, d_1..d_4) = 40 B written + one read (N=1, I=5).
 # SURVEY.md §8(d) quotes 48 B records (96 B/step) because it counts the record's start time; with a fixed
 # step the time grid is regenerated, so the start time carries no information and is not stored.  The
@@ -174,7 +174,7 @@ def dde_leg(d, torch, local_rank, K=3, W=2):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                      "frac": achieved / hbm, "traffic": DDE_DRAM_TRAFFIC_PER_LAUNCH,
                      "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch, "
-                                       "profiles/r1_run9_ncu_full_dde_fixed_v5.txt (algorithmic bytes per launch: "
+                                       "profiles/r1_final_ncu_full_dde_fixed.txt (algorithmic bytes per launch: "
                                        f"{int(DDE_BYTES_PER_STEP * steps)})",
                      "peak_source": src,
                      "algorithmic_bytes_per_rk_step": DDE_BYTES_PER_STEP,

@@ -29,6 +29,14 @@ inline void check(int rc) {
   if (rc != DFB_OK) throw Error(rc, dfb_last_error());
 }
 
+// A user system built into a plugin shared object: returns the system id
+// `equation(...)` takes.
+inline int register_user_system(const std::string& so_path) {
+  int32_t id = 0;
+  check(dfb_register_plugin(so_path.c_str(), &id));
+  return int(id);
+}
+
 // rk.rs constructors
 struct RK {
   static dfb_tableau by_name(const char* name) {

@@ -47,7 +47,9 @@ def build_user_system(header, struct_name, out_dir=None, force=False, verbose=Fa
     out_dir = os.path.abspath(out_dir or os.path.join(os.path.dirname(header), "_build"))
     obj_dir = os.path.join(out_dir, f"{struct_name}_{tag}_obj")
     so = os.path.join(out_dir, f"libdfb_user_{struct_name}_{tag}.so")
-    newest_dep = max(os.path.getmtime(os.path.join(r, f)) for r, _, fs in os.walk(CSRC) for f in fs)
+    # kernel sources the plugin is compiled from (csrc/host is the C++ builder mirror: not a dependency)
+    newest_dep = max(os.path.getmtime(os.path.join(r, f)) for r, _, fs in os.walk(CSRC) for f in fs
+                     if os.path.basename(r) != "host" and f != "api.cu")
     newest_dep = max(newest_dep, os.path.getmtime(os.path.join(CSRC, "..", "..", "include", "diffurch_b200.h")))
     if not force and os.path.exists(so) and os.path.getmtime(so) >= max(newest_dep, os.path.getmtime(header)):
         return so

@@ -235,7 +235,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    n_sample = 2048 * cores
+    n_sample = int(os.environ.get("DFB_BENCH_REF_SAMPLE", 2048 * cores))  # members per step (tests shrink it)
     for _ in range(args.warmup):
         cpu_oracle_rate(max(64, n_sample // 8), cores)
     rates, times = [], []

@@ -414,7 +414,7 @@ def main():
     # ---- CPU baseline (oracle "port"), bounded sample on this box's host cores ----
     cores = os.cpu_count() or 1
     probe_rate, _, _ = cpu_oracle_rate(256 * cores, cores)       # sizes the sample for ~15 s of CPU work
-    n_sample = int(max(1024 * cores, min(N_MEMBERS, 15.0 * probe_rate / STEPS_PER_MEMBER)))
+    n_sample = int(max(1024 * cores, min(N_MEMBERS, float(os.environ.get("DFB_BENCH_CPU_SECONDS", "15")) * probe_rate / STEPS_PER_MEMBER)))
     n_sample -= n_sample % cores
     cpu_rate, cpu_dt, _ = cpu_oracle_rate(n_sample, cores)
     cpu1_rate, _, _ = cpu_oracle_rate(64, 1)

@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -31,3 +33,26 @@ def test_reference_arm_prints_one_json_line():
 
 def test_reference_arm_other_ranks_are_silent():
     assert run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
+
+
+@pytest.mark.gpu
+def test_native_arm_json_line_has_every_contract_key():
+    env = dict(os.environ, DFB_BENCH_SKIP_DDE="1", DFB_BENCH_SKIP_OTHERS="1", DFB_BENCH_CPU_SECONDS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "2", "--warmup", "3",
+                        "--members", "65536"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["scaling"] == "weak"
+    assert d["vs_baseline"] is None and d["dtype"] == "f64" and "workload" in d["config"]
+    assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert d["e2e"]["h2d_bytes_per_step"] == 65536 * 6 * 8 and d["e2e"]["d2h_bytes_per_step"] == 65536 * 4 * 8
+    assert 0 < d["e2e"]["value"] <= d["value"] * 1.001
+    assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    assert 0.0 < d["roofline"]["frac"] <= 1.0 and d["roofline"]["unit"] == "TFLOP/s"
+    assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] == "port"
+    assert d["gpu_launches"] == 2 and set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}

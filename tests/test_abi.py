@@ -100,3 +100,28 @@ def test_solver_consumed_by_run_and_builder_semantics():
     assert [p2.loc[i].dedup for i in range(2)] == [1, 1]
     assert p2.loc[1].detection == abi.DET_BELOW_ZERO and p2.loc[1].location == abi.LOCATE_BISECTION
     assert p2.loc[1].callback_id == 1 and p2.loc[0].callback_id == abi.CB_NONE
+
+
+def test_ctypes_layout_equals_the_c_header(tmp_path):
+    """sizeof / offsetof of every struct of include/diffurch_b200.h, as gcc lays it out, against the
+    ctypes mirror (and therefore, through tests/test_rust_sys_matches_abi.py, the Rust bindings)."""
+    import ctypes as C
+    import subprocess
+    structs = {"dfb_tableau": abi.Tableau, "dfb_locator": abi.Locator, "dfb_auto_stepsize": abi.AutoStepsize,
+               "dfb_problem": abi.Problem, "dfb_system_info": abi.SystemInfo, "dfb_stats": abi.Stats,
+               "dfb_totals": abi.Totals}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "diffurch_b200.h"', "int main(void) {"]
+    for name, ct in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in ct._fields_:
+            lines.append(f'  printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, ct in structs.items():
+        assert int(out[name]) == C.sizeof(ct), name
+        for field, _ in ct._fields_:
+            assert int(out[f"{name}.{field}"]) == getattr(ct, field).offset, f"{name}.{field}"

@@ -785,18 +785,18 @@ int dfb_synchronize(dfb_handle* h) {
   return DFB_OK;
 }
 
+// Enqueues the download on the handle's stream; the caller synchronises once at the end (the
+// staging buffer is reused by the next download, which stream order makes safe).
 static int download_aos(dfb_handle* h, const double* d_soa, double* host, int width) {
   const size_t n = h->n;
   if (width == 1) {
     DFB_CUDA(cudaMemcpyAsync(host, d_soa, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    DFB_CUDA(cudaStreamSynchronize(h->stream));
     return DFB_OK;
   }
   const int block = 256;
   soa_to_aos_kernel<<<unsigned((n + block - 1) / block), block, 0, h->stream>>>(d_soa, h->d_stage, n, width);
   DFB_CUDA(cudaGetLastError());
   DFB_CUDA(cudaMemcpyAsync(host, h->d_stage, n * width * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  DFB_CUDA(cudaStreamSynchronize(h->stream));
   return DFB_OK;
 }
 
@@ -808,6 +808,7 @@ int dfb_get_final(dfb_handle* h, double* t, double* y, double* aux) {
   if (t && (rc = download_aos(h, h->d_t, t, 1)) != DFB_OK) return rc;
   if (y && (rc = download_aos(h, h->d_y, y, h->info.n_state)) != DFB_OK) return rc;
   if (aux && h->info.n_aux && (rc = download_aos(h, h->d_aux, aux, h->info.n_aux)) != DFB_OK) return rc;
+  DFB_CUDA(cudaStreamSynchronize(h->stream));
   return DFB_OK;
 }
 

@@ -123,11 +123,18 @@ class Ensemble:
     def synchronize(self):
         check(lib.dfb_synchronize(self._h))
 
-    def final(self, want_aux=True):
+    def final(self, want_aux=True, out=None):
+        """Final State of every member: (t [n], p [n, N], aux [n, A]).  `out=(t, p)` or `(t, p, aux)`
+        reuses caller-owned arrays (e.g. pinned host memory, so the download is a true async DMA)."""
         n, N, A = self.n, self.system.n_state, self.system.n_aux
-        t = np.empty(n)
-        y = np.empty((n, N))
-        aux = np.zeros((n, A)) if (A and want_aux) else None
+        if out is not None:
+            t, y = out[0], out[1]
+            assert t.shape == (n,) and y.shape == (n, N) and t.dtype == y.dtype == np.float64
+            aux = out[2] if (len(out) > 2 and A and want_aux) else (np.zeros((n, A)) if (A and want_aux) else None)
+        else:
+            t = np.empty(n)
+            y = np.empty((n, N))
+            aux = np.zeros((n, A)) if (A and want_aux) else None
         check(lib.dfb_get_final(self._h, _dptr(t), _dptr(y), _dptr(aux) if aux is not None else None))
         return t, y, (aux if aux is not None else np.zeros((n, 0)))
 

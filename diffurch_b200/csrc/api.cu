@@ -604,7 +604,7 @@ int dfb_run(dfb_handle* h, void* stream_v) {
   // Hot path: fixed step, no locators, no history, final state only.
   const bool no_start_cb = p.on_start_callback_id == DFB_CB_NONE;
   const bool hot_eligible = no_start_cb && p.stepsize_kind == DFB_STEP_FIXED && p.n_loc == 0 &&
-                            !h->info.uses_history && p.trace_every == 0 && p.max_steps == 0 &&
+                            !h->info.uses_history && p.max_steps == 0 &&
                             p.history_id == DFB_HIST_CONSTANT && !std::getenv("DFB_FORCE_GENERAL");
   h->kernel_kind = DFB_KERNEL_GENERAL;
   if (hot_eligible) {
@@ -613,8 +613,10 @@ int dfb_run(dfb_handle* h, void* stream_v) {
     if (h->info.n_aux) DFB_CUDA(cudaMemsetAsync(h->d_aux, 0, n * h->info.n_aux * sizeof(double), stream));
     DFB_CUDA(cudaEventRecord(h->ev0, stream));
     const DfbOdeFixedFn shim = T.ode_fixed;
+    const bool tracing = h->d_trace_t && p.trace_every > 0;
     const int rc = !shim ? -1 : shim(p.system_id, p.rk, p.t0, p.t1, p.h, n, y0, params, h->d_t, h->d_y,
-                        h->d_steps, h->d_rhs, h->d_status, stream);
+                        h->d_steps, h->d_rhs, h->d_status, tracing ? p.trace_every : 0, p.trace_capacity,
+                        tracing ? h->d_trace_t : nullptr, h->d_trace_y, h->d_nsamples, stream);
     if (rc > 0) return fail(DFB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(cudaError_t(rc)));
     if (rc == 0) {
       DFB_CUDA(cudaEventRecord(h->ev1, stream));

@@ -158,6 +158,25 @@ struct OdeFixedStepper {
   }
 
   // gid[u] = trajectory of slot u (clamped for the ragged tail; `valid` masks the stores)
+  // Output policy standing in for an `on_step` closure (solver.rs:290, 309): every k-th invocation
+  // stores (t, p) into the [capacity][1 + N][n] trace, one coalesced row per component.  The time
+  // grid is shared, so whether this invocation is sampled is the same for the whole grid.
+  __device__ __forceinline__ void on_step(const size_t* gid, const bool* valid, unsigned long long calls,
+                                          uint32_t& n_samples) {
+    if (calls % (unsigned long long)A.trace_every == 0 && n_samples < uint32_t(A.trace_capacity)) {
+      const size_t n_traj = A.n_traj;
+#pragma unroll
+      for (int u = 0; u < TPT; ++u) {
+        if (!valid[u]) continue;
+        A.trace_t[size_t(n_samples) * n_traj + gid[u]] = t_curr;
+#pragma unroll
+        for (int n = 0; n < N; ++n) A.trace_y[(size_t(n_samples) * N + n) * n_traj + gid[u]] = p_curr[u][n];
+      }
+      ++n_samples;
+    }
+  }
+
+  template <bool TRACE = false>
   __device__ void run(const size_t* gid, const bool* valid) {
     const size_t n_traj = A.n_traj;
 #pragma unroll
@@ -172,6 +191,8 @@ struct OdeFixedStepper {
     }
     t_curr = t_prev = A.t0;
     unsigned long long n_steps = 0;
+    uint32_t n_samples = 0u;
+    if (TRACE) on_step(gid, valid, 0ull, n_samples);  // events_on_step at t_init (solver.rs:290)
     if (t_curr < A.t1) {
       rhs_all(d_curr);  // first make_step evaluates k[0] itself (state.rs:97-98)
       const double h = A.h;
@@ -182,11 +203,13 @@ struct OdeFixedStepper {
       while (t_curr < A.t1 && (A.t1 - t_curr) >= h) {
         step<true>(h);
         ++n_steps;
+        if (TRACE) on_step(gid, valid, n_steps, n_samples);
       }
 #pragma unroll 1
       while (t_curr < A.t1) {
         step<false>(fmin(h, A.t1 - t_curr));
         ++n_steps;
+        if (TRACE) on_step(gid, valid, n_steps, n_samples);
       }
     }
 #pragma unroll
@@ -202,11 +225,13 @@ struct OdeFixedStepper {
       A.steps[gid[u]] = n_steps;
       A.rhs_evals[gid[u]] = n_steps > 0 ? n_steps * S + 1 : 0;
       A.status[gid[u]] = finite ? 0u : uint32_t(DFB_TRAJ_NONFINITE);
+      if (TRACE && A.n_samples) A.n_samples[gid[u]] = n_samples;
     }
   }
 };
 
-template <class Sys, int S, unsigned long long AMASK, unsigned BMASK, bool PRESCALED, int BLOCK, int TPT>
+template <class Sys, int S, unsigned long long AMASK, unsigned BMASK, bool PRESCALED, int BLOCK, int TPT,
+          bool TRACE = false>
 __global__ void __launch_bounds__(BLOCK)
     ode_fixed_kernel(const __grid_constant__ OdeFixedArgs A) {
   // slot u of thread g handles trajectory g + u * (threads in the grid): coalesced for every u
@@ -222,7 +247,7 @@ __global__ void __launch_bounds__(BLOCK)
   }
   if (!valid[0]) return;
   OdeFixedStepper<Sys, S, AMASK, BMASK, PRESCALED, TPT> st(A);
-  st.run(gid, valid);
+  st.template run<TRACE>(gid, valid);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -18,20 +18,40 @@ constexpr int kBlock = 128;
 template <class Sys, int S>
 constexpr int default_tpt() { return (Sys::N * (S + 3) <= 40) ? 2 : 1; }
 
-template <class Sys, int S, unsigned long long AMASK, unsigned BMASK>
+// TRACEABLE: also instantiate the variant that samples the trajectory (Trace output policy); kept to
+// the two tableaux people integrate with (rktp64, rk4) to bound the number of instantiations — a
+// traced run with another tableau takes the general kernel.
+template <class Sys, int S, unsigned long long AMASK, unsigned BMASK, bool TRACEABLE = false>
 bool try_launch(int S_rt, unsigned long long amask, unsigned bmask, const OdeFixedArgs& A,
                 cudaStream_t stream, int* rc) {
   if (S_rt != S) return false;
   if ((amask & ~AMASK) != 0ull || (bmask & ~BMASK) != 0u) return false;  // kernel must cover every non-zero
+  const bool trace = A.trace_every > 0;
+  if (trace && !TRACEABLE) return false;
   int tpt = default_tpt<Sys, S>();
   if (const char* e = getenv("DFB_ODE_TPT")) tpt = atoi(e) == 2 ? 2 : 1;
   if (Sys::N * (S + 3) > 40) tpt = 1;
   const size_t per_block = size_t(kBlock) * tpt;
   const size_t grid = (A.n_traj + per_block - 1) / per_block;
   if (tpt == 2) {
-    if constexpr (Sys::N * (S + 3) <= 40)
+    if constexpr (Sys::N * (S + 3) <= 40) {
+      if constexpr (TRACEABLE) {
+        if (trace) {
+          ode_fixed_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 2, true><<<unsigned(grid), kBlock, 0, stream>>>(A);
+          *rc = int(cudaGetLastError());
+          return true;
+        }
+      }
       ode_fixed_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 2><<<unsigned(grid), kBlock, 0, stream>>>(A);
+    }
   } else {
+    if constexpr (TRACEABLE) {
+      if (trace) {
+        ode_fixed_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 1, true><<<unsigned(grid), kBlock, 0, stream>>>(A);
+        *rc = int(cudaGetLastError());
+        return true;
+      }
+    }
     ode_fixed_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 1><<<unsigned(grid), kBlock, 0, stream>>>(A);
   }
   *rc = int(cudaGetLastError());
@@ -42,9 +62,9 @@ bool try_launch(int S_rt, unsigned long long amask, unsigned bmask, const OdeFix
 template <class Sys>
 bool launch_common(int S, unsigned long long am, unsigned bm, const OdeFixedArgs& A,
                    cudaStream_t st, int* rc) {
-  return try_launch<Sys, 7, amask_full_lower(7), 0x7Du>(S, am, bm, A, st, rc) ||  // rktp64
+  return try_launch<Sys, 7, amask_full_lower(7), 0x7Du, true>(S, am, bm, A, st, rc) ||  // rktp64
          try_launch<Sys, 7, amask_full_lower(7), 0x7Fu>(S, am, bm, A, st, rc) ||
-         try_launch<Sys, 4, kMaskRk4, 0xFu>(S, am, bm, A, st, rc) ||              // rk4
+         try_launch<Sys, 4, kMaskRk4, 0xFu, true>(S, am, bm, A, st, rc) ||        // rk4
          try_launch<Sys, 4, amask_full_lower(4), 0xFu>(S, am, bm, A, st, rc);
 }
 template <class Sys>
@@ -179,11 +199,17 @@ void fill_args(OdeFixedArgs& A, unsigned long long* amask_out, unsigned* bmask_o
 int run_ode_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h,
                        size_t n, const double* y0, const double* params, double* t_final,
                        double* y_final, unsigned long long* steps, unsigned long long* rhs_evals,
-                       uint32_t* status, cudaStream_t stream) {
+                       uint32_t* status, int trace_every, int trace_capacity, double* trace_t,
+                       double* trace_y, uint32_t* n_samples, cudaStream_t stream) {
   OdeFixedArgs A;
   unsigned long long amask = 0;
   unsigned bmask = 0;
   fill_args(A, &amask, &bmask, rk, t0, t1, h, n, y0, params, t_final, y_final, steps, rhs_evals, status);
+  A.trace_every = (trace_t && trace_capacity > 0) ? trace_every : 0;
+  A.trace_capacity = trace_capacity;
+  A.trace_t = trace_t;
+  A.trace_y = trace_y;
+  A.n_samples = n_samples;
   return launch_ode_fixed(system_id, rk.S, amask, bmask, A, stream);
 }
 

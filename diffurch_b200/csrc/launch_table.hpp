@@ -9,7 +9,8 @@
 typedef int (*DfbOdeFixedFn)(int system_id, const dfb_tableau& rk, double t0, double t1, double h, size_t n,
                              const double* y0, const double* params, double* t_final, double* y_final,
                              unsigned long long* steps, unsigned long long* rhs_evals, uint32_t* status,
-                             cudaStream_t stream);
+                             int trace_every, int trace_capacity, double* trace_t, double* trace_y,
+                             uint32_t* n_samples, cudaStream_t stream);
 typedef int (*DfbOdePeriodicFn)(int system_id, const dfb_tableau& rk, double t0, double t1, double h, size_t n,
                                 const double* y0, const double* params, double* t_final, double* y_final,
                                 double* aux_final, unsigned long long* steps, unsigned long long* events,
@@ -55,7 +56,7 @@ struct DfbLaunchTable {
   namespace NS {                                                                                     \
   int run_ode_fixed_shim(int, const dfb_tableau&, double, double, double, size_t, const double*,    \
                          const double*, double*, double*, unsigned long long*, unsigned long long*, \
-                         uint32_t*, cudaStream_t);                                                   \
+                         uint32_t*, int, int, double*, double*, uint32_t*, cudaStream_t);            \
   int run_ode_fixed_periodic_shim(int, const dfb_tableau&, double, double, double, size_t,          \
                                   const double*, const double*, double*, double*, double*,          \
                                   unsigned long long*, unsigned long long*, unsigned long long*,    \
@@ -70,7 +71,7 @@ struct DfbLaunchTable {
   }
 
 // What a plugin's `dfb_plugin_describe` fills in (csrc/plugin_entry.cu).
-#define DFB_PLUGIN_ABI 3
+#define DFB_PLUGIN_ABI 4
 struct dfb_plugin_desc {
   int plugin_abi;
   int n_state, n_params, n_aux, n_detectors, n_callbacks, uses_history;

@@ -32,7 +32,8 @@ int run_dde_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t
                        double max_delay, int history_id, int ring_capacity, size_t n,
                        const double* y0, const double* params, double* ring, double* t_final,
                        double* y_final, unsigned long long* steps, unsigned long long* rhs_evals,
-                       uint32_t* status, cudaStream_t stream);
+                       uint32_t* status, int trace_every, int trace_capacity, double* trace_t,
+                       double* trace_y, uint32_t* n_samples, cudaStream_t stream);
 size_t dde_fixed_ring_doubles(int n_state, int I, int capacity);
 int run_ode_adaptive_shim(int system_id, const dfb_tableau& rk, const dfb_auto_stepsize& ctl, double t0,
                           double t1, size_t n, const double* y0, const double* params, double* t_final,
@@ -486,7 +487,7 @@ int dfb_create(const dfb_problem* desc, size_t n_traj, int device, dfb_handle** 
     h->dde_hot = info->uses_history && desc->arith == DFB_ARITH_FAST &&
                  desc->on_start_callback_id == DFB_CB_NONE &&
                  desc->stepsize_kind == DFB_STEP_FIXED && desc->n_loc == 0 && desc->n_disco == 0 &&
-                 desc->trace_every == 0 && desc->max_steps == 0 && shape_ok &&
+                 desc->max_steps == 0 && shape_ok &&
                  dde_hot_system(desc->system_id) && table_for(desc->system_id, DFB_ARITH_FAST).dde_fixed &&
                  std::isfinite(desc->max_delay) && desc->max_delay > 0.0 &&
                  desc->max_delay / desc->h < 60000.0 && !std::getenv("DFB_FORCE_GENERAL");
@@ -707,10 +708,12 @@ int dfb_run(dfb_handle* h, void* stream_v) {
     DFB_CUDA(cudaMemsetAsync(h->d_rejected, 0, n * sizeof(unsigned long long), stream));
     DFB_CUDA(cudaMemsetAsync(h->d_events, 0, n * sizeof(unsigned long long), stream));
     DFB_CUDA(cudaEventRecord(h->ev0, stream));
+    const bool dde_tracing = h->d_trace_t && p.trace_every > 0;
     const int rc = !T.dde_fixed ? -1 : T.dde_fixed(p.system_id, p.rk, p.t0, p.t1, p.h, p.max_delay,
                                                 p.history_id, h->ring_capacity, n, y0, params,
                                                 h->d_ring_coeff, h->d_t, h->d_y, h->d_steps, h->d_rhs,
-                                                h->d_status, stream);
+                                                h->d_status, dde_tracing ? p.trace_every : 0, p.trace_capacity,
+                                                dde_tracing ? h->d_trace_t : nullptr, h->d_trace_y, h->d_nsamples, stream);
     if (rc > 0) return fail(DFB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(cudaError_t(rc)));
     if (rc < 0) return fail(DFB_ERR_UNSUPPORTED, "no DDE hot-path kernel for this tableau");
     DFB_CUDA(cudaEventRecord(h->ev1, stream));

@@ -57,6 +57,11 @@ struct DdeFixedArgs {
   unsigned long long* rhs_evals;
   uint32_t* status;
   double* ring;  // [cap][ceil(n/32)][N*I][32]
+  // Trace output policy (on_step closures, solver.rs:290, 309); trace_every = 0: off
+  int32_t trace_every, trace_capacity;
+  double* trace_t;      // [cap][n]
+  double* trace_y;      // [cap][N][n]
+  uint32_t* n_samples;  // [n]
 };
 
 // ---- cp.async (LDGSTS) helpers: global -> shared without staging registers; completion is
@@ -150,6 +155,7 @@ struct DdeFixedStepper {
   double t_old1;          // its successor on the grid (t_deque[1])
   int w;
   uint32_t status;
+  uint32_t n_samples = 0u;
   bool loaded, uniform;
   bool track_oldest;  // max_delay < tau: "deleted time range" panics (state.rs:166-171) are possible
   unsigned warp_base, slot_stride;  // ring addressing in doubles: [slot][warp][F][32] (host guarantees < 2^32)
@@ -330,6 +336,18 @@ struct DdeFixedStepper {
     // next step's t_prev, so only lookups the reference rejects as "not yet computed" select it.
   }
 
+  // every trace_every-th on_step invocation stores (t, p); the grid is shared, the test is uniform
+  __device__ __forceinline__ void on_step(unsigned calls) {
+    if (A.trace_every > 0 && calls % unsigned(A.trace_every) == 0u && n_samples < uint32_t(A.trace_capacity)) {
+      if (valid) {
+        A.trace_t[size_t(n_samples) * A.n_traj + gid] = t_curr;
+#pragma unroll
+        for (int n = 0; n < N; ++n) A.trace_y[(size_t(n_samples) * N + n) * A.n_traj + gid] = p_curr[n];
+      }
+      ++n_samples;
+    }
+  }
+
   __device__ void run() {
     const size_t n_traj = A.n_traj;
 #pragma unroll
@@ -368,6 +386,8 @@ struct DdeFixedStepper {
       }
     }
     int s = 0;  // index of the step being taken = ring record it will write
+    n_samples = 0u;
+    on_step(0u);  // events_on_step at t_init (solver.rs:290)
     // A trajectory that hits one of the reference's panics keeps stepping (its warp must
     // stay converged for the cooperative staging); its status word records the panic.
     if (t_curr < A.t1) {
@@ -385,6 +405,7 @@ struct DdeFixedStepper {
         commit<true>(s, h);
         refill(s, tau, h);
         ++s;
+        on_step(unsigned(s));
       }
       // Phase B (steady): full steps whose lookups all lie after t_init and before the
       // last committed time.  What the reference checks on every lookup is checked once
@@ -397,6 +418,7 @@ struct DdeFixedStepper {
         commit<true>(s, h);
         refill(s, tau, h);
         ++s;
+        on_step(unsigned(s));
       }
       // closing partial step(s): checked path
 #pragma unroll 1
@@ -406,6 +428,7 @@ struct DdeFixedStepper {
         commit<false>(s, h_req);
         refill(s, tau, h);
         ++s;
+        on_step(unsigned(s));
       }
     }
     cp_async_wait<0>();
@@ -420,6 +443,7 @@ struct DdeFixedStepper {
     A.steps[gid] = (unsigned long long)s;
     A.rhs_evals[gid] = s > 0 ? (unsigned long long)s * S + 1 : 0;
     A.status[gid] = status;
+    if (A.trace_every > 0 && A.n_samples) A.n_samples[gid] = n_samples;
   }
 };
 

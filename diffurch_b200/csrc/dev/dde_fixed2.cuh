@@ -72,6 +72,20 @@ struct DdeFixedStepperT {
   double k[TPT][S][N];
   double prm[TPT][NP];
   uint32_t status[TPT];
+  uint32_t n_samples = 0u;
+
+  __device__ __forceinline__ void on_step(unsigned calls) {  // see DdeFixedStepper::on_step
+    if (A.trace_every > 0 && calls % unsigned(A.trace_every) == 0u && n_samples < uint32_t(A.trace_capacity)) {
+#pragma unroll
+      for (int u = 0; u < TPT; ++u) {
+        if (!valid[u]) continue;
+        A.trace_t[size_t(n_samples) * A.n_traj + gid[u]] = t_curr;
+#pragma unroll
+        for (int n = 0; n < N; ++n) A.trace_y[(size_t(n_samples) * N + n) * A.n_traj + gid[u]] = p_curr[u][n];
+      }
+      ++n_samples;
+    }
+  }
 
   __device__ DdeFixedStepperT(const DdeFixedArgs& A_, double* sm_) : A(A_), lane(int(threadIdx.x & 31)), sm(sm_) {}
 
@@ -259,6 +273,7 @@ struct DdeFixedStepperT {
       }
     }
     int s = 0;
+    on_step(0u);  // events_on_step at t_init (solver.rs:290)
     if (t_curr < A.t1) {
 #pragma unroll
       for (int u = 0; u < TPT; ++u) rhs<false>(u, d_curr[u]);  // k[0] of the first step (state.rs:97-98)
@@ -274,6 +289,7 @@ struct DdeFixedStepperT {
         commit<true>(s, h);
         refill(s, tau, h);
         ++s;
+        on_step(unsigned(s));
       }
       // Phase B (steady)
 #pragma unroll 1
@@ -286,6 +302,7 @@ struct DdeFixedStepperT {
         commit<true>(s, h);
         refill(s, tau, h);
         ++s;
+        on_step(unsigned(s));
       }
       // closing partial step(s): checked path
 #pragma unroll 1
@@ -295,6 +312,7 @@ struct DdeFixedStepperT {
         commit<false>(s, h_req);
         refill(s, tau, h);
         ++s;
+        on_step(unsigned(s));
       }
     }
     cp_async_wait<0>();
@@ -311,6 +329,7 @@ struct DdeFixedStepperT {
       A.steps[gid[u]] = (unsigned long long)s;
       A.rhs_evals[gid[u]] = s > 0 ? (unsigned long long)s * S + 1 : 0;
       A.status[gid[u]] = status[u];
+      if (A.trace_every > 0 && A.n_samples) A.n_samples[gid[u]] = n_samples;
     }
   }
 };

@@ -79,7 +79,8 @@ int run_dde_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t
                        double max_delay, int history_id, int ring_capacity, size_t n,
                        const double* y0, const double* params, double* ring, double* t_final,
                        double* y_final, unsigned long long* steps, unsigned long long* rhs_evals,
-                       uint32_t* status, cudaStream_t stream) {
+                       uint32_t* status, int trace_every, int trace_capacity, double* trace_t,
+                       double* trace_y, uint32_t* n_samples, cudaStream_t stream) {
   DdeFixedArgs A;
   std::memset(&A, 0, sizeof(A));
   unsigned long long am = 0, bim = 0;
@@ -142,6 +143,11 @@ int run_dde_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t
   A.rhs_evals = rhs_evals;
   A.status = status;
   A.ring = ring;
+  A.trace_every = (trace_t && trace_capacity > 0) ? trace_every : 0;
+  A.trace_capacity = trace_capacity;
+  A.trace_t = trace_t;
+  A.trace_y = trace_y;
+  A.n_samples = n_samples;
   int rc = 0;
   bool ok = false;
 #ifdef DFB_PLUGIN_SYSTEM

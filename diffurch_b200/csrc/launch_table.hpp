@@ -34,7 +34,8 @@ typedef int (*DfbDdeFixedFn)(int system_id, const dfb_tableau& rk, double t0, do
                              double max_delay, int history_id, int ring_capacity, size_t n, const double* y0,
                              const double* params, double* ring, double* t_final, double* y_final,
                              unsigned long long* steps, unsigned long long* rhs_evals, uint32_t* status,
-                             cudaStream_t stream);
+                             int trace_every, int trace_capacity, double* trace_t, double* trace_y,
+                             uint32_t* n_samples, cudaStream_t stream);
 typedef int (*DfbGeneralFn)(const DevProblem& P, int system_id, bool has_loc, const LaunchCfg& c,
                             int locate_batch_threshold);
 
@@ -71,7 +72,7 @@ struct DfbLaunchTable {
   }
 
 // What a plugin's `dfb_plugin_describe` fills in (csrc/plugin_entry.cu).
-#define DFB_PLUGIN_ABI 4
+#define DFB_PLUGIN_ABI 5
 struct dfb_plugin_desc {
   int plugin_abi;
   int n_state, n_params, n_aux, n_detectors, n_callbacks, uses_history;

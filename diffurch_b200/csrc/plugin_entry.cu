@@ -15,7 +15,7 @@ DFB_DECLARE_SHIMS(dfb_fast)
 namespace dfb_fast {
 int run_dde_fixed_shim(int, const dfb_tableau&, double, double, double, double, int, int, size_t, const double*,
                        const double*, double*, double*, double*, unsigned long long*, unsigned long long*,
-                       uint32_t*, cudaStream_t);
+                       uint32_t*, int, int, double*, double*, uint32_t*, cudaStream_t);
 int run_ode_adaptive_shim(int, const dfb_tableau&, const dfb_auto_stepsize&, double, double, size_t,
                           const double*, const double*, double*, double*, unsigned long long*,
                           unsigned long long*, unsigned long long*, uint32_t*, unsigned long long*, int,

@@ -471,6 +471,32 @@ def test_dde_hot_path_delay_is_an_exact_multiple_of_the_step(oracle):
             assert np.max(np.abs(f.p - o.p)) < 1e-11, (system.name, tau, h)
 
 
+def test_dde_hot_path_trace_policy(oracle):
+    # Trace (every k-th on_step call, capacity-bounded) inside both DDE hot kernels: the time grid and
+    # the sample counts are the oracle's bit for bit, the samples within the FAST tolerance, the last
+    # sample (stride 1) is the final state of the untraced run.
+    k = 0.5 + np.arange(165) / 164.0              # ragged: 5 warps + 5 members
+    for tpt in ("1", "2"):
+        os.environ["DFB_DDE_TPT"] = tpt
+        try:
+            for every, cap, t1 in ((1, 600, 10.0), (7, 600, 10.0), (3, 50, 10.0), (1, 600, 0.03)):
+                mk = lambda arith: cases.eq_dde_sin(k=k, t1=t1, trace=False, arith=arith).on_step(d.Trace(every, cap))
+                g = mk("fast").run()
+                assert g.totals["kernel_kind"] == d.abi.KERNEL_DDE_FIXED and np.all(g.status == 0)
+                o = oracle.run_solver(mk("strict"), n_threads=8)
+                assert np.array_equal(g.steps, o.steps)
+                assert np.array_equal(g.trace_n, o.trace_n)
+                n = int(g.trace_n[0])
+                assert np.all(g.trace_n == n)
+                assert np.array_equal(g.trace_t[:, :n], o.trace_t[:, :n])
+                assert np.max(np.abs(g.trace_p[:, :n] - o.trace_p[:, :n])) < 1e-12, (tpt, every, cap)
+                if every == 1 and cap > n:
+                    plain = cases.eq_dde_sin(k=k, t1=t1, trace=False, arith="fast").run()
+                    assert np.array_equal(g.trace_p[:, n - 1, :], plain.p) and np.array_equal(g.p, plain.p)
+        finally:
+            del os.environ["DFB_DDE_TPT"]
+
+
 def test_dde_hot_path_panics_become_status_bits(oracle):
     mk = lambda: cases.eq_dde_sin(trace=False, arith="fast").stepsize(1.5)   # delay <= h
     g, o = mk().run(), oracle.run_solver(mk())

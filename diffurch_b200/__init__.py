@@ -12,5 +12,6 @@ from .rk import RK, ButcherTableau, ButcherTableu  # noqa: F401
 from .solver import (Ensemble, EnsembleState, EventLog, Solver, Trace,  # noqa: F401
                      default_problem)
 from .stepsize import AutomaticStepsize  # noqa: F401
+from . import lyapunov  # noqa: F401,E402
 
 __version__ = "0.1.0"

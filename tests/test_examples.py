@@ -32,5 +32,7 @@ def test_examples_run_and_give_the_documented_results():
     st = run("ode_linear_3_fibonacci")
     t, x = st.trace_t[0, :st.trace_n[0]], st.trace_p[0, :st.trace_n[0], 0]
     assert abs(x[np.argmax(t == 10.0)] - 55.0) < 1e-6 and abs(x[np.argmax(t == 20.0)] - 6765.0) < 1e-3
+    lam, a, b, worst = run("ndde_lyapunov_grid", na=16, nb=8, t1=100.0, check=8)
+    assert lam.shape == (128,) and np.all(np.isfinite(lam)) and worst < 2e-3
     st = run("user_system_van_der_pol", n=64)
     assert np.all(st.status == 0) and np.all(st.aux[:, 0] >= 8)

@@ -135,3 +135,37 @@ def test_two_gpu_lyapunov_spectra_gather(tmp_path):
     assert np.array_equal(got["y_all"], one.p)
     # the three exponents sum to the trace of the Jacobian, -(sigma + 1 + beta)
     assert np.max(np.abs(got["spectra"].sum(axis=1) + (10.0 + 1.0 + 8.0 / 3.0))) < 1e-6
+
+
+def _ndde_worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import diffurch_b200 as d
+    from diffurch_b200 import lyapunov
+    a, b = [x.ravel() for x in np.meshgrid(np.linspace(-2.0, 0.5, 33), np.linspace(-0.6, 0.6, 31))]
+    lam = lyapunov.sharded_leading_exponents(d.systems.NddeLinear, a, b, rank, world, device="cuda", t1=60.0)
+    if rank == 0:
+        np.save(out_path, lam)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_two_gpu_ndde_lyapunov_grid_gather(tmp_path):
+    # BASELINE configs[4] on a delay-equation grid: exponents of a ragged 1023-member grid, sharded 512 + 511
+    import torch.multiprocessing as mp
+    import diffurch_b200 as d
+    from diffurch_b200 import lyapunov
+    out = str(tmp_path / "lam.npy")
+    mp.spawn(_ndde_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    a, b = [x.ravel() for x in np.meshgrid(np.linspace(-2.0, 0.5, 33), np.linspace(-0.6, 0.6, 31))]
+    solver, window = lyapunov.linear_delay_grid(d.systems.NddeLinear, a, b, t1=60.0)
+    st = solver.run()
+    one = lyapunov.leading_exponent(st.trace_t, st.trace_p, st.trace_n, window, t_skip=20.0)
+    assert np.array_equal(np.load(out), one)

@@ -15,6 +15,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import cases  # noqa: E402
 import diffurch_b200 as d  # noqa: E402
+from diffurch_b200 import lyapunov  # noqa: E402
 
 
 def timed(make, reps=2):
@@ -63,6 +64,9 @@ def main():
         "dde_relay_clamp_2^16_t30_strict": lambda: relay_clamp(n_ly, "strict"),
         "lorenz_2^16_adaptive_with_events_fast": lambda: cases.lorenz(n=n_ly, t1=20.0, arith="fast").stepsize(
             d.AutomaticStepsize(1e-2, (1e-6, 1e-1), [1e-9] * 3, [1e-9] * 3, 4, 0.9, (0.2, 5.0))).on(d.Periodic(0.5, 0.0), None),
+        "ndde_lyapunov_grid_2^16_t100_traced_every5_fast": lambda: lyapunov.linear_delay_grid(
+            d.systems.NddeLinear, *[x.ravel() for x in np.meshgrid(np.linspace(-2.0, 0.5, 256),
+                                                                     np.linspace(-0.6, 0.6, max(1, n_ly // 256)))])[0],
         "dde_sin_2^16_t20_traced_every50_fast": lambda: cases.eq_dde_sin(
             k=0.5 + np.arange(n_ly) / n_ly, t1=20.0, trace=False, arith="fast").on_step(d.Trace(50, 24)),
         "lorenz_2^18_t10_traced_every25_fast": lambda: cases.lorenz(n=n_lo // 4, t1=10.0, arith="fast",

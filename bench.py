@@ -216,6 +216,10 @@ def other_config_legs(d, peak_tflops):
         # configs[4]: Lorenz + 3x3 variational block (N = 12), QR every 0.5; flop/step by the same
         # formula as the headline: 12(2*21+6) + 12*13 + 13 + 7*F_rhs, F_rhs = 8 + 45 + 1
         "lyapunov_lorenz_2^18_rho_grid_t=[0,100]": (lambda: cases.lyap_lorenz(100.0, rho=np.linspace(20.0, 40.0, 1 << 18), arith="fast"), 1123.0),
+        # configs[4] on a delay-equation grid: x' = a x(t-1) + b x'(t-1), every 5th step sampled for the
+        # segment-norm exponent estimator (diffurch_b200/lyapunov.py); the kernel time is what is reported
+        "lyapunov_ndde_2^16_ab_grid_t=[0,100]": (lambda: d.lyapunov.linear_delay_grid(
+            d.systems.NddeLinear, *[x.ravel() for x in np.meshgrid(np.linspace(-2.0, 0.5, 256), np.linspace(-0.6, 0.6, 256))])[0], None),
     }
     for name, (mk, flops) in legs.items():
         try:

@@ -39,7 +39,8 @@ int run_ode_adaptive_shim(int system_id, const dfb_tableau& rk, const dfb_auto_s
                           double t1, size_t n, const double* y0, const double* params, double* t_final,
                           double* y_final, unsigned long long* steps, unsigned long long* rejected,
                           unsigned long long* rhs_evals, uint32_t* status, unsigned long long* queue,
-                          int n_sm, cudaStream_t stream);
+                          int n_sm, int trace_every, int trace_capacity, double* trace_t, double* trace_y,
+                          uint32_t* n_samples, cudaStream_t stream);
 }
 
 namespace {
@@ -681,9 +682,9 @@ int dfb_run(dfb_handle* h, void* stream_v) {
   }
 
   // Adaptive hot path (dev/ode_adaptive.cuh): AutomaticStepsize, no locators, no history,
-  // final state only, FAST arithmetic.
+  // final state or a Trace, FAST arithmetic.
   const bool adaptive_eligible = no_start_cb && p.stepsize_kind == DFB_STEP_AUTOMATIC && p.n_loc == 0 &&
-                                 !h->info.uses_history && p.trace_every == 0 && p.max_steps == 0 &&
+                                 !h->info.uses_history && p.max_steps == 0 &&
                                  p.history_id == DFB_HIST_CONSTANT && p.arith == DFB_ARITH_FAST &&
                                  !std::getenv("DFB_FORCE_GENERAL");
   if (adaptive_eligible) {
@@ -691,9 +692,12 @@ int dfb_run(dfb_handle* h, void* stream_v) {
     if (h->info.n_aux) DFB_CUDA(cudaMemsetAsync(h->d_aux, 0, n * h->info.n_aux * sizeof(double), stream));
     DFB_CUDA(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned long long), stream));
     DFB_CUDA(cudaEventRecord(h->ev0, stream));
+    const bool tracing = h->d_trace_t && p.trace_every > 0;
     const int rc = !T.ode_adaptive ? -1 : T.ode_adaptive(p.system_id, p.rk, p.automatic, p.t0, p.t1, n, y0, params,
                                                    h->d_t, h->d_y, h->d_steps, h->d_rejected, h->d_rhs,
-                                                   h->d_status, h->d_queue, h->n_sm, stream);
+                                                   h->d_status, h->d_queue, h->n_sm, tracing ? p.trace_every : 0,
+                                                   p.trace_capacity, tracing ? h->d_trace_t : nullptr,
+                                                   h->d_trace_y, h->d_nsamples, stream);
     if (rc > 0) return fail(DFB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(cudaError_t(rc)));
     if (rc == 0) {
       DFB_CUDA(cudaEventRecord(h->ev1, stream));

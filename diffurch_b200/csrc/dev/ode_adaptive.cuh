@@ -49,6 +49,11 @@ struct OdeAdaptiveArgs {
   unsigned long long* rhs_evals;
   uint32_t* status;
   unsigned long long* queue;  // next unassigned trajectory (zeroed before the launch)
+  // Trace output policy (on_step closures, solver.rs:290, 309); read by the TRACE instantiations
+  int32_t trace_every, trace_capacity;
+  double* trace_t;      // [cap][n]
+  double* trace_y;      // [cap][N][n]
+  uint32_t* n_samples;  // [n]
 };
 
 // 1/x for a positive, normal x: MUFU.RCP64H seed + two Newton steps (relative error ~1e-16).
@@ -103,7 +108,7 @@ __device__ __forceinline__ bool in_root_range(double x) {
 }
 
 // P = order + 1 when it is one of the compiled exponents, else 0 (run-time exponent A.p)
-template <class Sys, int S, unsigned long long AMASK, unsigned BMASK, unsigned EMASK, int TPT, int P>
+template <class Sys, int S, unsigned long long AMASK, unsigned BMASK, unsigned EMASK, int TPT, int P, bool TRACE = false>
 struct OdeAdaptiveStepper {
   static constexpr int N = Sys::N;
   static constexpr int NP = Sys::NP > 0 ? Sys::NP : 1;
@@ -117,12 +122,26 @@ struct OdeAdaptiveStepper {
   double prm[TPT][NP];
   unsigned n_steps[TPT], n_rej[TPT];  // per trajectory; 2^32 attempts of one member is beyond any run
   uint32_t flags[TPT];
+  unsigned n_samp[TPT];
   NoHist nohist;
 
   __device__ explicit OdeAdaptiveStepper(const OdeAdaptiveArgs& A_) : A(A_) {}
 
   __device__ __forceinline__ void rhs(int u, double tt, const double* y, double* out) {
     Sys::rhs(Ref{tt, y, d[u], tt, y, &nohist}, prm[u], out);
+  }
+
+  // on_step: the n_steps-th invocation (0 = the initial state) is stored when n_steps % every == 0.
+  // Every member has its own time grid, so the rows are member-indexed, not warp-uniform.
+  __device__ __forceinline__ void sample(int u) {
+    if (!TRACE) return;
+    if (active[u] && n_steps[u] % unsigned(A.trace_every) == 0u && n_samp[u] < unsigned(A.trace_capacity)) {
+      const size_t n_traj = A.n_traj, i = idx[u];
+      A.trace_t[size_t(n_samp[u]) * n_traj + i] = t[u];
+#pragma unroll
+      for (int n = 0; n < N; ++n) A.trace_y[(size_t(n_samp[u]) * N + n) * n_traj + i] = p[u][n];
+      ++n_samp[u];
+    }
   }
 
   __device__ void fetch(int u) {
@@ -142,6 +161,8 @@ struct OdeAdaptiveStepper {
     h_auto[u] = A.ctl.stepsize;
     n_steps[u] = n_rej[u] = 0u;
     flags[u] = 0u;
+    n_samp[u] = 0u;
+    sample(u);  // events_on_step at t_init (solver.rs:290)
     if (t[u] < A.t1) rhs(u, t[u], p[u], d[u]);  // k[0] of the first make_step (state.rs:97-98)
   }
 
@@ -159,6 +180,7 @@ struct OdeAdaptiveStepper {
     // as the reference evaluates: S per attempt, k[0] once at the start and once after every undo
     A.rhs_evals[i] = attempts > 0 ? attempts * S + 1 + n_rej[u] : 0;
     A.status[i] = flags[u] | (finite ? 0u : uint32_t(DFB_TRAJ_NONFINITE));
+    if (TRACE) A.n_samples[i] = n_samp[u];
   }
 
   // one attempted step for every slot (make_step + StepsizeController::update + commit/undo)
@@ -269,6 +291,7 @@ struct OdeAdaptiveStepper {
             p[u][n] = y[u][n];
             d[u][n] = d_new[n];
           }
+          sample(u);
         }
       } else {
         ++n_steps[u];
@@ -278,6 +301,7 @@ struct OdeAdaptiveStepper {
           p[u][n] = y[u][n];
           d[u][n] = d_new[n];
         }
+        sample(u);
       }
       h_auto[u] = h_next;
     }
@@ -311,10 +335,11 @@ struct OdeAdaptiveStepper {
   }
 };
 
-template <class Sys, int S, unsigned long long AMASK, unsigned BMASK, unsigned EMASK, int BLOCK, int TPT, int P>
+template <class Sys, int S, unsigned long long AMASK, unsigned BMASK, unsigned EMASK, int BLOCK, int TPT, int P,
+          bool TRACE = false>
 __global__ void __launch_bounds__(BLOCK)
     ode_adaptive_kernel(const __grid_constant__ OdeAdaptiveArgs A) {
-  OdeAdaptiveStepper<Sys, S, AMASK, BMASK, EMASK, TPT, P> st(A);
+  OdeAdaptiveStepper<Sys, S, AMASK, BMASK, EMASK, TPT, P, TRACE> st(A);
   st.run();
 }
 

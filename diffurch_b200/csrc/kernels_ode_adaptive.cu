@@ -34,6 +34,12 @@ bool try_launch(int S_rt, unsigned long long am, unsigned bm, unsigned em, const
   static_assert(Sys::pure_rhs, "the adaptive hot path needs a right-hand side that depends on (t, p, params) only");
   if (S_rt != S) return false;
   if ((am & ~AMASK) || (bm & ~BMASK) || (em & ~EMASK)) return false;
+  if (A.trace_every > 0) {  // Trace policy: one-slot instantiations only
+    if (A.p == 5) launch_grid(ode_adaptive_kernel<Sys, S, AMASK, BMASK, EMASK, kBlock, 1, 5, true>, A, 1, n_sm, stream);
+    else launch_grid(ode_adaptive_kernel<Sys, S, AMASK, BMASK, EMASK, kBlock, 1, 0, true>, A, 1, n_sm, stream);
+    *rc = int(cudaGetLastError());
+    return true;
+  }
   int tpt = default_tpt<Sys, S>();
   if (const char* e = getenv("DFB_ADAPT_TPT")) tpt = atoi(e) == 2 ? 2 : 1;
   if (Sys::N * (S + 3) > 40) tpt = 1;
@@ -73,7 +79,8 @@ int run_ode_adaptive_shim(int system_id, const dfb_tableau& rk, const dfb_auto_s
                           double t1, size_t n, const double* y0, const double* params, double* t_final,
                           double* y_final, unsigned long long* steps, unsigned long long* rejected,
                           unsigned long long* rhs_evals, uint32_t* status, unsigned long long* queue,
-                          int n_sm, cudaStream_t stream) {
+                          int n_sm, int trace_every, int trace_capacity, double* trace_t, double* trace_y,
+                          uint32_t* n_samples, cudaStream_t stream) {
   OdeAdaptiveArgs A;
   std::memset(&A, 0, sizeof(A));
   unsigned long long am = 0;
@@ -106,6 +113,11 @@ int run_ode_adaptive_shim(int system_id, const dfb_tableau& rk, const dfb_auto_s
   A.rhs_evals = rhs_evals;
   A.status = status;
   A.queue = queue;
+  A.trace_every = (trace_t && trace_capacity > 0) ? trace_every : 0;
+  A.trace_capacity = trace_capacity;
+  A.trace_t = trace_t;
+  A.trace_y = trace_y;
+  A.n_samples = n_samples;
   int rc = 0;
   bool ok = false;
 #ifdef DFB_PLUGIN_SYSTEM

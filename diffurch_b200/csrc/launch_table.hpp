@@ -29,7 +29,8 @@ typedef int (*DfbOdeAdaptiveFn)(int system_id, const dfb_tableau& rk, const dfb_
                                 double t1, size_t n, const double* y0, const double* params, double* t_final,
                                 double* y_final, unsigned long long* steps, unsigned long long* rejected,
                                 unsigned long long* rhs_evals, uint32_t* status, unsigned long long* queue,
-                                int n_sm, cudaStream_t stream);
+                                int n_sm, int trace_every, int trace_capacity, double* trace_t, double* trace_y,
+                                uint32_t* n_samples, cudaStream_t stream);
 typedef int (*DfbDdeFixedFn)(int system_id, const dfb_tableau& rk, double t0, double t1, double h,
                              double max_delay, int history_id, int ring_capacity, size_t n, const double* y0,
                              const double* params, double* ring, double* t_final, double* y_final,
@@ -72,7 +73,7 @@ struct DfbLaunchTable {
   }
 
 // What a plugin's `dfb_plugin_describe` fills in (csrc/plugin_entry.cu).
-#define DFB_PLUGIN_ABI 5
+#define DFB_PLUGIN_ABI 6
 struct dfb_plugin_desc {
   int plugin_abi;
   int n_state, n_params, n_aux, n_detectors, n_callbacks, uses_history;

@@ -19,7 +19,7 @@ int run_dde_fixed_shim(int, const dfb_tableau&, double, double, double, double, 
 int run_ode_adaptive_shim(int, const dfb_tableau&, const dfb_auto_stepsize&, double, double, size_t,
                           const double*, const double*, double*, double*, unsigned long long*,
                           unsigned long long*, unsigned long long*, uint32_t*, unsigned long long*, int,
-                          cudaStream_t);
+                          int, int, double*, double*, uint32_t*, cudaStream_t);
 }
 
 #define DFB_STR2(x) #x

@@ -625,6 +625,44 @@ def test_adaptive_hot_path_harmonic_vs_oracle(oracle):
     assert np.max(np.abs(f.steps.astype(np.int64) - gen.steps.astype(np.int64))) <= 1
 
 
+def test_adaptive_hot_path_trace_policy(oracle):
+    # Trace inside the adaptive hot kernel: every member has its own time grid.  Sample counts follow
+    # from the step counts, the last sample (stride 1) is the final state, every sample lies within
+    # the solver tolerance of the exact solution, and members whose step counts equal the oracle's
+    # have the oracle's sample times within the controller's sensitivity.
+    amp = 1.0 + np.arange(257) / 64.0
+    y0 = np.stack([np.zeros(257), amp], axis=1)
+    for every, cap in ((1, 4096), (5, 4096), (2, 20)):
+        def mk(arith="fast"):
+            return (d.Solver.new().initial(y0).equation(d.systems.Harmonic).interval(0.0, 10.0)
+                    .stepsize(auto_stepsize(2)).arith(arith).on_step(d.Trace(every, cap)))
+        f = mk().run()
+        assert f.totals["kernel_kind"] == KERNEL_ODE_ADAPTIVE and np.all(f.status == 0)
+        assert np.array_equal(f.trace_n, np.minimum(f.steps // every + 1, cap))
+        o = oracle.run_solver(mk("strict"), n_threads=8)
+        same = np.flatnonzero((f.steps == o.steps) & (f.rejected == o.rejected))
+        assert same.size > 200
+        for i in same[::16]:
+            n = int(f.trace_n[i])
+            assert n == int(o.trace_n[i])
+            # the error estimate is a difference of O(1e-9) quantities: FMA contraction moves it by
+            # ~1e-7 relative, hence the step sizes by ~1e-10 each, accumulating along the grid
+            assert np.max(np.abs(f.trace_t[i, :n] - o.trace_t[i, :n])) < 1e-5
+            assert np.max(np.abs(f.trace_p[i, :n] - o.trace_p[i, :n])) < 1e-4
+        for i in range(0, 257, 8):
+            n = int(f.trace_n[i])
+            t = f.trace_t[i, :n]
+            assert t[0] == 0.0 and np.all(np.diff(t) > 0)
+            assert np.max(np.abs(f.trace_p[i, :n, 0] - amp[i] * np.sin(t))) < 1e-6
+        if every == 1:
+            n = f.trace_n
+            assert np.array_equal(f.trace_t[np.arange(257), n - 1], f.t)
+            assert np.array_equal(f.trace_p[np.arange(257), n - 1, :], f.p)
+            plain = (d.Solver.new().initial(y0).equation(d.systems.Harmonic).interval(0.0, 10.0)
+                     .stepsize(auto_stepsize(2)).arith("fast").run())
+            assert np.array_equal(plain.p, f.p) and np.array_equal(plain.steps, f.steps)
+
+
 @pytest.mark.parametrize("rk,order", [("rktp64", 4), ("rk43", 3), ("rk4", 2), ("heun2", 1), ("three_eights", 2)])
 def test_adaptive_hot_path_tableaux(oracle, rk, order):
     lam = -0.5 - np.arange(100) / 50.0

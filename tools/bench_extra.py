@@ -71,6 +71,8 @@ def main():
             k=0.5 + np.arange(n_ly) / n_ly, t1=20.0, trace=False, arith="fast").on_step(d.Trace(50, 24)),
         "lorenz_2^18_t10_traced_every25_fast": lambda: cases.lorenz(n=n_lo // 4, t1=10.0, arith="fast",
                                                                      trace=d.Trace(25, 104)),
+        "lorenz_2^18_adaptive_traced_every25_fast": lambda: cases.lorenz(n=n_lo // 4, t1=10.0, arith="fast", trace=d.Trace(25, 104)).stepsize(
+            d.AutomaticStepsize(1e-2, (1e-6, 1e-1), [1e-9] * 3, [1e-9] * 3, 4, 0.9, (0.2, 5.0))),
         "lorenz_2^20_rk4_fast": lambda: cases.lorenz(n=n_lo, t1=50.0, arith="fast", rk=d.RK.rk4()),
         "lorenz_2^20_rktp64_strict": lambda: cases.lorenz(n=n_lo, t1=50.0, arith="strict"),
     }

@@ -392,6 +392,78 @@ def test_fuzz_fast_arithmetic_within_tolerance(oracle, seed):
         assert np.max(np.abs(g.p - o.p)) < 1e-9, what
 
 
+@pytest.mark.parametrize("seed", range(12 * SCALE))
+def test_fuzz_traced_hot_kernels_fast_vs_oracle(oracle, seed):
+    # Trace(every, capacity) inside the fixed-step, DDE (one and two members per thread) and adaptive hot
+    # kernels, FAST arithmetic, against the STRICT oracle: sample counts and the shared time grid bit for
+    # bit, samples within the FAST tolerance
+    rng = np.random.default_rng(21000 + seed)
+    n = int(rng.choice([1, 31, 32, 33, 64, 65, 127, 129, 200, 257]))
+    every, cap = int(rng.integers(1, 9)), int(rng.choice([1, 2, 7, 40, 400, 4000]))
+    which = int(rng.integers(0, 3))
+    import cases
+    if which == 0:      # fixed-step ODE: traceable instantiations are rktp64 and rk4
+        rk, rk_name = [(d.RK.rktp64(), "rktp64"), (d.RK.rk4(), "rk4")][rng.integers(0, 2)]
+        system, prm, y0 = [(d.systems.Harmonic, None, rng.uniform(-2, 2, (n, 2))),
+                           (d.systems.Linear1, rng.uniform(-2, 0.5, (n, 1)), rng.uniform(0.5, 2, (n, 1)))][rng.integers(0, 2)]
+        h = float(rng.choice([0.1, 0.03, 1.0 / 64]))
+        t1 = float(rng.uniform(5.0, 300.0)) * h
+
+        def mk(arith):
+            s = d.Solver.new().initial(y0).interval(0.0, t1).stepsize(h).rk(rk).arith(arith).on_step(d.Trace(every, cap))
+            return s.equation(system, prm) if prm is not None else s.equation(system)
+        kind, tol = abi.KERNEL_ODE_FIXED, 1e-12
+        what = f"[seed {seed}: {system.name} n={n} rk={rk_name} h={h} t1={t1} every={every} cap={cap}]"
+    elif which == 1:    # constant-delay DDE / NDDE
+        k = rng.uniform(0.4, 1.4, n)
+        tau = float(rng.choice([1.0, 0.5, 0.73]))
+        h = float(rng.choice([0.02, 0.05, 0.011]))
+        rk, rk_name = [(d.RK.rktp64(), "rktp64"), (d.RK.rk43(), "rk43"), (d.RK.rk4(), "rk4")][rng.integers(0, 3)]
+        if rng.random() < 0.4:
+            prm, system, init = cases.ndde_params(k, tau), d.systems.NddeLinear, d.InitFn(d.SIN, d.SIN_DERIV)
+        else:
+            prm, system, init = cases.dde_params(k, tau), d.systems.DdeLinear, d.InitFn(d.SIN)
+        t1 = float(rng.uniform(0.5, 6.0))
+        tpt = str(rng.integers(1, 3))
+
+        def mk(arith):
+            return (d.Solver.new().max_delay(tau).initial(init).interval(0.0, t1).stepsize(h).rk(rk)
+                    .equation(system, prm).arith(arith).on_step(d.Trace(every, cap)))
+        kind, tol = abi.KERNEL_DDE_FIXED, 1e-11
+        what = f"[seed {seed}: {system.name} n={n} tau={tau} h={h} rk={rk_name} t1={t1} every={every} cap={cap} tpt={tpt}]"
+        os.environ["DFB_DDE_TPT"] = tpt
+    else:               # adaptive: every member has its own grid; consistency + exact solution
+        amp = rng.uniform(0.5, 3.0, n)
+        y0 = np.stack([np.zeros(n), amp], 1)
+        ctl = d.AutomaticStepsize(1e-2, (1e-6, 1e-1), [1e-9] * 2, [1e-9] * 2, 4, 0.9, (0.2, 5.0))
+        t1 = float(rng.uniform(0.5, 8.0))
+        f = (d.Solver.new().initial(y0).equation(d.systems.Harmonic).interval(0.0, t1).stepsize(ctl)
+             .arith("fast").on_step(d.Trace(every, cap)).run())
+        what = f"[seed {seed}: adaptive harmonic n={n} t1={t1} every={every} cap={cap}]"
+        assert f.totals["kernel_kind"] == abi.KERNEL_ODE_ADAPTIVE and np.all(f.status == 0), what
+        assert np.array_equal(f.trace_n, np.minimum(f.steps // every + 1, cap)), what
+        for i in range(0, n, 7):
+            m = int(f.trace_n[i])
+            t = f.trace_t[i, :m]
+            assert t[0] == 0.0 and np.all(np.diff(t) > 0) and t[-1] <= t1, what
+            assert np.max(np.abs(f.trace_p[i, :m, 0] - amp[i] * np.sin(t))) < 1e-6, what
+        return
+    try:
+        g = mk("fast").run()
+    finally:
+        os.environ.pop("DFB_DDE_TPT", None)
+    o = oracle.run_solver(mk("strict"), n_threads=4)
+    assert g.totals["kernel_kind"] == kind and np.all(g.status == 0), what
+    assert np.array_equal(g.steps, o.steps) and np.array_equal(g.t, o.t), what
+    assert np.array_equal(g.trace_n, o.trace_n) and np.all(g.trace_n <= cap), what
+    m = int(g.trace_n[0])
+    assert np.all(g.trace_n == m), what
+    assert np.array_equal(g.trace_t[:, :m], o.trace_t[:, :m]), what
+    scale = np.maximum(np.abs(o.trace_p[:, :m]), 1.0)
+    assert np.max(np.abs(g.trace_p[:, :m] - o.trace_p[:, :m]) / scale) < tol, what
+    assert np.max(np.abs(g.p - o.p) / np.maximum(np.abs(o.p), 1.0)) < tol, what
+
+
 def test_fuzz_reached_every_ode_kernel_family():
     # runs last in this file: the random configurations above must have exercised these kernels
     if not SEEN:

@@ -125,7 +125,7 @@ def test_lorenz_hot_path_equals_general_path(oracle):
         del os.environ["DFB_FORCE_GENERAL"]
     assert np.array_equal(hot.p, gen.p) and np.array_equal(hot.t, gen.t)
     assert np.array_equal(hot.steps, gen.steps) and np.array_equal(hot.rhs_evals, gen.rhs_evals)
-    # trace forces the general kernel too; its last sample is the final state
+    # a traced run (rktp64: the hot kernel's TRACE instantiation); its last sample is the final state
     tr = cases.lorenz(n=300, t1=3.0, trace=d.Trace(1, 800)).run()
     assert np.array_equal(tr.p, hot.p)
     n = tr.trace_n[0]

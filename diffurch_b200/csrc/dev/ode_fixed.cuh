@@ -425,8 +425,8 @@ struct OdeFixedPeriodicStepper : OdeFixedStepper<Sys, S, AMASK, BMASK, PRESCALED
   }
 };
 
-template <class Sys, int S, unsigned long long AMASK, unsigned BMASK, bool PRESCALED, int BLOCK, int TPT>
-__global__ void __launch_bounds__(BLOCK)
+template <class Sys, int S, unsigned long long AMASK, unsigned BMASK, bool PRESCALED, int BLOCK, int TPT, int MINB = 1>
+__global__ void __launch_bounds__(BLOCK, MINB)
     ode_fixed_periodic_kernel(const __grid_constant__ OdeFixedArgs A) {
   const size_t g = size_t(blockIdx.x) * BLOCK + threadIdx.x;
   const size_t stride = size_t(gridDim.x) * BLOCK;

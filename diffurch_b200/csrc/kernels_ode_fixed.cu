@@ -86,7 +86,26 @@ bool try_launch_periodic(int S_rt, unsigned long long amask, unsigned bmask, con
   if (S_rt != S) return false;
   if ((amask & ~AMASK) != 0ull || (bmask & ~BMASK) != 0u) return false;
   const size_t grid = (A.n_traj + kBlock - 1) / kBlock;
-  ode_fixed_periodic_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 1><<<unsigned(grid), kBlock, 0, stream>>>(A);
+  // Wide states (the 12-component Lyapunov system) take 218 registers uncapped: 8 resident warps
+  // per SM, latency-bound (ncu: FP64 pipe 75 % active, 0.7 eligible warps per cycle).  Capped at 200
+  // registers in 64-thread blocks (10 warps) the pipe saturates: 216.6 -> 208.9 ms on the 2^18-member
+  // Lorenz spectrum batch; 168 registers (12 warps) gives the same time.  DFB_PERIODIC_MINB=1|3|5|6
+  // selects the build (tuning).
+  bool wide = false;
+  if constexpr (Sys::N >= 8) {
+    const char* e = getenv("DFB_PERIODIC_MINB");
+    const int m = e ? atoi(e) : 5;
+    wide = m == 3 || m == 5 || m == 6;
+    const size_t grid64 = (A.n_traj + 63) / 64;
+    if (m == 3)
+      ode_fixed_periodic_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 1, 3><<<unsigned(grid), kBlock, 0, stream>>>(A);
+    else if (m == 5)
+      ode_fixed_periodic_kernel<Sys, S, AMASK, BMASK, kPrescaled, 64, 1, 5><<<unsigned(grid64), 64, 0, stream>>>(A);
+    else if (m == 6)
+      ode_fixed_periodic_kernel<Sys, S, AMASK, BMASK, kPrescaled, 64, 1, 6><<<unsigned(grid64), 64, 0, stream>>>(A);
+  }
+  if (!wide)
+    ode_fixed_periodic_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 1><<<unsigned(grid), kBlock, 0, stream>>>(A);
   *rc = int(cudaGetLastError());
   return true;
 }

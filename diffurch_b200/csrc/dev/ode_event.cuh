@@ -25,6 +25,9 @@
 //  * dynamic trajectory assignment (global work counter) as in ode_adaptive.cuh: members stop at
 //    different times (egg billiard: after 200 reflections), finished lanes pull the next member.
 #pragma once
+#ifndef DFB_EV_UNROLL
+#define DFB_EV_UNROLL 1
+#endif
 #include "common.cuh"
 #include "integrator.cuh"
 #include "ode_fixed.cuh"
@@ -448,7 +451,8 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
       // finish inside the burst idle for at most inner_steps - 1 rounds (they would wait for the
       // batch anyway), and the vote / batching / refill logic is paid once per burst.
       if (!locate_round) {
-#pragma unroll 1
+        constexpr int kBurstUnroll = DFB_EV_UNROLL;
+#pragma unroll kBurstUnroll
         for (int it = 0; it < A.inner_steps; ++it) {
           if (it > 0) {
             if (__ballot_sync(0xffffffffu, mode == MODE_STEP || mode == MODE_EVENT_RESTEP) == 0u) break;

@@ -128,12 +128,14 @@ DDE_BYTES_PER_STEP = 80.0
 DDE_BYTES_SURVEY_PER_STEP = 96.0
 
 
-def dde_leg(d, torch, local_rank, K=3, W=2):
+def dde_leg(d, torch, local_rank, K=3, W=2, rank=0, world=1):
     """Secondary workload (BASELINE configs[2]): 2^18-member constant-delay DDE
-    x' = a x + b x(t-1), k sweep, rktp64, h = 0.02, t in [0, 100]; HBM-bound."""
+    x' = a x + b x(t-1), k sweep, rktp64, h = 0.02, t in [0, 100]; HBM-bound.
+    Under torchrun every rank integrates its own 2^18-member range of the (world x 2^18)-member
+    sweep (weak scaling, no data-path collective); the time is the max over ranks."""
     import cases
     n = DDE_MEMBERS
-    k = 0.5 + np.arange(n) / (n - 1.0)
+    k = 0.5 + (rank * n + np.arange(n)) / (n * world - 1.0)
     prm = cases.dde_params(k)
     problem = (d.Solver.new().max_delay(1.0).initial(d.InitFn(d.SIN)).interval(0.0, 100.0)
                .stepsize(0.02).equation(d.systems.DdeLinear, prm).arith("fast").problem())
@@ -157,29 +159,49 @@ def dde_leg(d, torch, local_rank, K=3, W=2):
     tot = ens.totals()
     t_fin, y_fin, _ = ens.final()
     err = float(np.max(np.abs(y_fin[:, 0] - np.sin(k * t_fin))))
-    steps = tot["steps"]
-    rate = steps / (float(np.mean(ms)) * 1e-3)
+    ens.close()
+    return {"mean_ms": float(np.mean(ms)), "err": err, "steps": int(tot["steps"]), "n_failed": int(tot["n_failed"])}
+
+
+def dde_report(local, world, torch, dist):
+    """Combine the ranks' DDE legs (max of the time and the error, sums of the counts).  The collectives
+    live here, outside the try block of the compute, so a rank whose leg failed still takes part."""
+    n = DDE_MEMBERS
+    ok = local is not None and "error" not in local
+    vals = [local["mean_ms"], local["err"], 0.0] if ok else [0.0, 0.0, 1.0]
+    sums = [float(local["steps"]), float(local["n_failed"])] if ok else [0.0, 0.0]
+    if world > 1:
+        mx = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        sm = torch.tensor(sums, dtype=torch.float64, device="cuda")
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        vals, sums = [float(x) for x in mx.tolist()], [float(x) for x in sm.tolist()]
+    if vals[2] != 0.0:
+        return local if (local is not None and "error" in local) else {"error": "the DDE leg failed on another rank"}
+    mean_ms, err = vals[0], vals[1]
+    steps, n_failed = int(sums[0]), int(sums[1])
+    rate = steps / (mean_ms * 1e-3)
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         hbm, src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     except Exception:
         hbm, src = 6650.0, "fallback 6.65 TB/s (of fallback)"
-    achieved = DDE_BYTES_PER_STEP * rate / 1e9
-    ens.close()
+    achieved = DDE_BYTES_PER_STEP * rate / 1e9 / world   # per GPU, against one GPU's copy bandwidth
     return {
-        "workload": "dde_linear_2^18_members_k_sweep_tau=1_rktp64_h=0.02_t=[0,100]",
-        "metric": "rk_steps_per_sec", "value": rate, "unit": "RK steps/s", "ms_per_step": float(np.mean(ms)),
-        "rk_steps_per_member": int(steps // n), "n_failed": int(tot["n_failed"]),
+        "workload": "dde_linear_2^18_members_per_gpu_k_sweep_tau=1_rktp64_h=0.02_t=[0,100]",
+        "metric": "rk_steps_per_sec", "value": rate, "unit": "RK steps/s", "ms_per_step": mean_ms,
+        "n_gpus": world, "scaling": "weak",
+        "rk_steps_per_member": int(steps // (n * world)), "n_failed": n_failed,
         "max_abs_err_vs_exact_sin": err,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                      "frac": achieved / hbm, "traffic": DDE_DRAM_TRAFFIC_PER_LAUNCH,
                      "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch, "
                                        "profiles/r1_final_ncu_full_dde_fixed.txt (algorithmic bytes per launch: "
-                                       f"{int(DDE_BYTES_PER_STEP * steps)})",
+                                       f"{int(DDE_BYTES_PER_STEP * steps // world)})",
                      "peak_source": src,
                      "algorithmic_bytes_per_rk_step": DDE_BYTES_PER_STEP,
                      "survey_bytes_per_rk_step": DDE_BYTES_SURVEY_PER_STEP,
-                     "frac_at_survey_bytes": DDE_BYTES_SURVEY_PER_STEP * rate / 1e9 / hbm,
+                     "frac_at_survey_bytes": DDE_BYTES_SURVEY_PER_STEP * rate / 1e9 / world / hbm,
                      "kernel": "dde_fixed2_kernel<SysDdeLinear,7,5,rktp64-sparsity> (two members per thread)"},
     }
 
@@ -379,6 +401,15 @@ def main():
     h2d = int(y0.nbytes + prm.nbytes)
     d2h = int(tf.nbytes + yf.nbytes)
 
+    # ---- secondary workload (configs[2]); every rank takes part, rank 0 reports ----
+    secondary = None
+    if not os.environ.get("DFB_BENCH_SKIP_DDE"):
+        try:
+            local_dde = dde_leg(d, torch, local_rank, rank=rank, world=world)
+        except Exception as e:  # the headline line must still print
+            local_dde = {"error": repr(e)}
+        secondary = dde_report(local_dde, world, torch, dist)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -430,13 +461,6 @@ def main():
                   f"CPU path (Rust toolchain unavailable), std::thread over members",
         "single_core_ns_per_step": 1e9 / cpu1_rate,
     }
-
-    secondary = None
-    if world == 1 and not os.environ.get("DFB_BENCH_SKIP_DDE"):
-        try:
-            secondary = dde_leg(d, torch, local_rank)
-        except Exception as e:  # the headline line must still print
-            secondary = {"error": repr(e)}
 
     others = None
     if world == 1 and not os.environ.get("DFB_BENCH_SKIP_OTHERS"):

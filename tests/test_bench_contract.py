@@ -56,3 +56,20 @@ def test_native_arm_json_line_has_every_contract_key():
     assert 0.0 < d["roofline"]["frac"] <= 1.0 and d["roofline"]["unit"] == "TFLOP/s"
     assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] == "port"
     assert d["gpu_launches"] == 2 and set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+def test_dde_leg_report_combines_ranks_and_survives_a_failed_rank():
+    # the collective part of the secondary (DDE) leg, on one rank: the arithmetic of the report and the
+    # error path (a failed leg must yield an error entry, never an exception: the headline still prints)
+    sys.path.insert(0, ROOT)
+    import importlib
+    bench = importlib.import_module("bench")
+    n = bench.DDE_MEMBERS
+    local = {"mean_ms": 18.5, "err": 1e-11, "steps": 5001 * n, "n_failed": 0}
+    rep = bench.dde_report(local, 1, None, None)
+    assert rep["n_gpus"] == 1 and rep["rk_steps_per_member"] == 5001 and rep["n_failed"] == 0
+    assert abs(rep["value"] - 5001 * n / 18.5e-3) < 1.0
+    rf = rep["roofline"]
+    assert rf["bound"] == "hbm" and abs(rf["achieved"] - bench.DDE_BYTES_PER_STEP * rep["value"] / 1e9) < 1e-6
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
+    assert bench.dde_report({"error": "boom"}, 1, None, None) == {"error": "boom"}

@@ -29,6 +29,9 @@
 
 namespace DFB_NS {
 
+constexpr uint32_t kDdePanicBits =
+    DFB_TRAJ_HISTORY_DELETED | DFB_TRAJ_HISTORY_NOT_READY | DFB_TRAJ_NO_DERIVATIVE;
+
 struct DdeFixedArgs {
   double a[DFB_MAX_STAGES * DFB_MAX_STAGES];
   double b[DFB_MAX_STAGES];
@@ -155,7 +158,7 @@ struct DdeFixedStepper {
   double t_old1;          // its successor on the grid (t_deque[1])
   int w;
   uint32_t status;
-  uint32_t n_samples = 0u;
+  uint32_t n_samples = 0u, n_samples_alive = 0u;
   bool loaded, uniform;
   bool track_oldest;  // max_delay < tau: "deleted time range" panics (state.rs:166-171) are possible
   unsigned warp_base, slot_stride;  // ring addressing in doubles: [slot][warp][F][32] (host guarantees < 2^32)
@@ -345,6 +348,8 @@ struct DdeFixedStepper {
         for (int n = 0; n < N; ++n) A.trace_y[(size_t(n_samples) * N + n) * A.n_traj + gid] = p_curr[n];
       }
       ++n_samples;
+      // the reference stops at a panic: what a panicked member stores from then on is not counted
+      if (!(status & kDdePanicBits)) n_samples_alive = n_samples;
     }
   }
 
@@ -386,7 +391,7 @@ struct DdeFixedStepper {
       }
     }
     int s = 0;  // index of the step being taken = ring record it will write
-    n_samples = 0u;
+    n_samples = n_samples_alive = 0u;
     on_step(0u);  // events_on_step at t_init (solver.rs:290)
     // A trajectory that hits one of the reference's panics keeps stepping (its warp must
     // stay converged for the cooperative staging); its status word records the panic.
@@ -443,7 +448,7 @@ struct DdeFixedStepper {
     A.steps[gid] = (unsigned long long)s;
     A.rhs_evals[gid] = s > 0 ? (unsigned long long)s * S + 1 : 0;
     A.status[gid] = status;
-    if (A.trace_every > 0 && A.n_samples) A.n_samples[gid] = n_samples;
+    if (A.trace_every > 0 && A.n_samples) A.n_samples[gid] = n_samples_alive;
   }
 };
 

@@ -72,7 +72,7 @@ struct DdeFixedStepperT {
   double k[TPT][S][N];
   double prm[TPT][NP];
   uint32_t status[TPT];
-  uint32_t n_samples = 0u;
+  uint32_t n_samples = 0u, n_samples_alive[TPT] = {};
 
   __device__ __forceinline__ void on_step(unsigned calls) {  // see DdeFixedStepper::on_step
     if (A.trace_every > 0 && calls % unsigned(A.trace_every) == 0u && n_samples < uint32_t(A.trace_capacity)) {
@@ -84,6 +84,9 @@ struct DdeFixedStepperT {
         for (int n = 0; n < N; ++n) A.trace_y[(size_t(n_samples) * N + n) * A.n_traj + gid[u]] = p_curr[u][n];
       }
       ++n_samples;
+#pragma unroll
+      for (int u = 0; u < TPT; ++u)
+        if (!(status[u] & kDdePanicBits)) n_samples_alive[u] = n_samples;
     }
   }
 
@@ -329,7 +332,7 @@ struct DdeFixedStepperT {
       A.steps[gid[u]] = (unsigned long long)s;
       A.rhs_evals[gid[u]] = s > 0 ? (unsigned long long)s * S + 1 : 0;
       A.status[gid[u]] = status[u];
-      if (A.trace_every > 0 && A.n_samples) A.n_samples[gid[u]] = n_samples;
+      if (A.trace_every > 0 && A.n_samples) A.n_samples[gid[u]] = n_samples_alive[u];
     }
   }
 };

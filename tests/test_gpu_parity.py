@@ -497,6 +497,28 @@ def test_dde_hot_path_trace_policy(oracle):
             del os.environ["DFB_DDE_TPT"]
 
 
+def test_dde_hot_path_trace_stops_counting_at_a_panic(oracle):
+    # the reference stops at a panic; a panicked member of the hot kernel keeps stepping (its warp stays
+    # converged) but its sample count is frozen where the reference's trace ends
+    k = 0.5 + np.arange(70) / 69.0
+    for tpt in ("1", "2"):
+        os.environ["DFB_DDE_TPT"] = tpt
+        try:
+            for must_panic, tweak in ((True, lambda s: s.stepsize(1.5)), (True, lambda s: s.max_delay(0.5)),
+                                      (False, lambda s: s.max_delay(0.97)), (False, lambda s: s.max_delay(0.9))):
+                mk = lambda arith: tweak(cases.eq_dde_sin(k=k, t1=4.0, trace=False, arith=arith)).on_step(d.Trace(1, 400))
+                g, o = mk("fast").run(), oracle.run_solver(mk("strict"), n_threads=4)
+                assert g.totals["kernel_kind"] == d.abi.KERNEL_DDE_FIXED
+                assert np.array_equal(g.status, o.status) and (np.any(o.status != 0) or not must_panic)
+                assert np.array_equal(g.trace_n, o.trace_n)
+                for i in range(0, 70, 9):
+                    n = int(g.trace_n[i])
+                    assert np.array_equal(g.trace_t[i, :n], o.trace_t[i, :n])
+                    assert np.max(np.abs(g.trace_p[i, :n] - o.trace_p[i, :n])) < 1e-12
+        finally:
+            del os.environ["DFB_DDE_TPT"]
+
+
 def test_dde_hot_path_panics_become_status_bits(oracle):
     mk = lambda: cases.eq_dde_sin(trace=False, arith="fast").stepsize(1.5)   # delay <= h
     g, o = mk().run(), oracle.run_solver(mk())

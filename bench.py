@@ -119,7 +119,7 @@ def cpu_oracle_rate(n_sample, threads):
 
 
 DDE_MEMBERS = 1 << 18
-DDE_DRAM_TRAFFIC_PER_LAUNCH = 51124647000 + 52019964000  # ncu, profiles/r1_final_ncu_full_dde_fixed.txt
+DDE_DRAM_TRAFFIC_PER_LAUNCH = 50509854000 + 51415350000  # ncu --set full, profiles/r1_final_ncu_full_dde_fixed.txt
 # Algorithmic bytes per RK step: one coefficient record (y, d_1..d_4) = 40 B written + one read (N=1, I=5).
 # SURVEY.md §8(d) quotes 48 B records (96 B/step) because it counts the record's start time; with a fixed
 # step the time grid is regenerated, so the start time carries no information and is not stored.  The

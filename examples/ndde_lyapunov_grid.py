@@ -47,3 +47,7 @@ def main(na=64, nb=64, t1=100.0, system=None, check=16):
 
 if __name__ == "__main__":
     main()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()

@@ -457,8 +457,10 @@ template <class Sys, int S, int I, unsigned long long AMASK, unsigned BMASK, uns
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
     dde_fixed_kernel(const __grid_constant__ DdeFixedArgs A) {
   using Stepper = DdeFixedStepper<Sys, S, I, AMASK, BMASK, BIMASK>;
-  __shared__ __align__(16) double smem[(BLOCK / 32) * kDdeSmemSlots * Stepper::kWarpRec];
-  const size_t g = size_t(blockIdx.x) * BLOCK + threadIdx.x;
+  // (blockDim.x / 32) * kDdeSmemSlots * kWarpRec doubles, sized by the launcher: BLOCK is the launch
+  // bound, the block itself is chosen from the ensemble size (host/launch_geometry.hpp)
+  extern __shared__ __align__(16) double smem[];
+  const size_t g = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   // every lane of a warp stays in the kernel (warp-cooperative staging); lanes past the
   // end replay the last trajectory and store nothing.  The ring is allocated for whole warps.
   if ((g & ~size_t(31)) >= A.n_traj) return;  // whole warp past the end (warp-uniform exit)

@@ -344,10 +344,10 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
   constexpr int TPT = 2;
   using StepperT = DdeFixedStepperT<Sys, S, I, AMASK, BMASK, BIMASK, TPT>;
   using Stepper1 = DdeFixedStepper<Sys, S, I, AMASK, BMASK, BIMASK>;
-  __shared__ __align__(16) double smem[(BLOCK / 32) * kDdeSmemSlots * TPT * StepperT::kWarpRec];
+  extern __shared__ __align__(16) double smem[];  // (blockDim.x / 32) * kDdeSmemSlots * TPT * kWarpRec doubles
   double* sm_warp = smem + (threadIdx.x / 32) * kDdeSmemSlots * TPT * StepperT::kWarpRec;
-  const size_t g0 = size_t(blockIdx.x) * BLOCK + threadIdx.x;
-  const size_t stride = size_t(gridDim.x) * BLOCK;
+  const size_t g0 = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
   if ((g0 & ~size_t(31)) >= A.n_traj) return;  // whole warp past the end in slot 0 (and then in slot 1 too)
   size_t g[TPT], gid[TPT];
   bool valid[TPT];

@@ -234,9 +234,10 @@ template <class Sys, int S, unsigned long long AMASK, unsigned BMASK, bool PRESC
           bool TRACE = false>
 __global__ void __launch_bounds__(BLOCK)
     ode_fixed_kernel(const __grid_constant__ OdeFixedArgs A) {
-  // slot u of thread g handles trajectory g + u * (threads in the grid): coalesced for every u
-  const size_t g = size_t(blockIdx.x) * BLOCK + threadIdx.x;
-  const size_t stride = size_t(gridDim.x) * BLOCK;
+  // slot u of thread g handles trajectory g + u * (threads in the grid): coalesced for every u.
+  // BLOCK is the launch bound; the host sizes the block (<= BLOCK) from the ensemble (host/launch_geometry.hpp).
+  const size_t g = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
   size_t gid[TPT];
   bool valid[TPT];
 #pragma unroll

@@ -39,21 +39,39 @@ bool try_launch(int S_rt, int I_rt, unsigned long long am, unsigned bm, unsigned
                 const DdeFixedArgs& A, cudaStream_t stream, int* rc) {
   if (S_rt != S || I_rt != I) return false;
   if ((am & ~AMASK) || (bm & ~BMASK) || (bim & ~BIMASK)) return false;
-  // two members per thread (dev/dde_fixed2.cuh) once the ensemble fills the device that way;
-  // DFB_DDE_TPT=1|2 overrides (tuning / tests)
+  // Members per thread and block size from the ensemble size.  The kernel is HBM-bound once the device
+  // is full (two members per thread: dev/dde_fixed2.cuh) and latency-bound below that: a small ensemble
+  // (a 2^18-member ensemble sharded over 8 GPUs is 1 024 warps for 592 SM sub-partitions) is spread over
+  // every SM in 32-thread blocks, one member per thread.  DFB_DDE_TPT=1|2 / DFB_DDE_BLOCK override (tuning).
+  using Stepper = DdeFixedStepper<Sys, S, I, AMASK, BMASK, BIMASK>;
+  auto kernel2 = dde_fixed2_kernel<Sys, S, I, AMASK, BMASK, BIMASK, kBlock, kMinBlocks2>;
+  auto kernel1 = dde_fixed_kernel<Sys, S, I, AMASK, BMASK, BIMASK, kBlock, kMinBlocks>;
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(kernel2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(kernel1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         int((kBlock / 32) * kDdeSmemSlots * 2 * Stepper::kWarpRec * sizeof(double)));
+    cudaFuncSetAttribute(kernel1, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         int((kBlock / 32) * kDdeSmemSlots * Stepper::kWarpRec * sizeof(double)));
+  }
+  const size_t warps = (A.n_traj + 31) / 32;
   int tpt = A.n_traj >= 65536 ? 2 : 1;
+  // below ~16 warps per SM one warp per block spreads the ensemble over every SM sub-partition
+  int block = warps >= size_t(n_sm) * 16 ? kBlock : (warps >= size_t(n_sm) * 8 ? 64 : 32);
   if (const char* e = getenv("DFB_DDE_TPT")) tpt = atoi(e) == 2 ? 2 : 1;
+  if (const char* e = getenv("DFB_DDE_BLOCK")) block = atoi(e) == 32 ? 32 : (atoi(e) == 64 ? 64 : kBlock);
   if (tpt == 2) {
-    const size_t grid = (A.n_traj + size_t(kBlock) * 2 - 1) / (size_t(kBlock) * 2);
-    auto kernel = dde_fixed2_kernel<Sys, S, I, AMASK, BMASK, BIMASK, kBlock, kMinBlocks2>;
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    kernel<<<unsigned(grid), kBlock, 0, stream>>>(A);
+    const size_t grid = (A.n_traj + size_t(block) * 2 - 1) / (size_t(block) * 2);
+    const size_t smem = size_t(block / 32) * kDdeSmemSlots * 2 * Stepper::kWarpRec * sizeof(double);
+    kernel2<<<unsigned(grid), block, smem, stream>>>(A);
   } else {
-    const size_t grid = (A.n_traj + kBlock - 1) / kBlock;
-    auto kernel = dde_fixed_kernel<Sys, S, I, AMASK, BMASK, BIMASK, kBlock, kMinBlocks>;
-    // the staging buffers of kMinBlocks resident blocks need the large shared-memory carveout
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    kernel<<<unsigned(grid), kBlock, 0, stream>>>(A);
+    const size_t grid = (A.n_traj + block - 1) / block;
+    const size_t smem = size_t(block / 32) * kDdeSmemSlots * Stepper::kWarpRec * sizeof(double);
+    kernel1<<<unsigned(grid), block, smem, stream>>>(A);
   }
   *rc = int(cudaGetLastError());
   return true;

@@ -2,6 +2,7 @@
 // Compiled twice (see dev/common.cuh): STRICT (-fmad=false) and FAST.
 #include "dev/ode_fixed.cuh"
 #include "launch.hpp"
+#include "host/launch_geometry.hpp"
 
 #include <cstdlib>
 #include <cstring>
@@ -13,10 +14,38 @@ constexpr unsigned long long kMaskRk4 = amask_bit(1, 0) | amask_bit(2, 1) | amas
 constexpr bool kPrescaled = (DFB_ARITH == 1);
 constexpr int kBlock = 128;
 
-// trajectories per thread: 2 where the doubled register footprint still fits
-// (N * (S + 3) doubles per trajectory), else 1.  DFB_ODE_TPT=1|2 overrides (tuning).
-template <class Sys, int S>
-constexpr int default_tpt() { return (Sys::N * (S + 3) <= 40) ? 2 : 1; }
+// (members per thread, block size) from the ensemble size: see host/launch_geometry.hpp.  Occupancy of
+// each variant is queried once per instantiation.
+template <auto kernel1, auto kernel2>
+dfb_host::LaunchGeometry pick_geometry(bool allow2, size_t n) {
+  static int occ1[3] = {0, 0, 0}, occ2[3] = {0, 0, 0}, n_sm = 0;
+  static const int blocks[3] = {128, 64, 32};
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    for (int b = 0; b < 3; ++b) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1[b], kernel1, blocks[b], 0);
+      if (allow2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2[b], kernel2, blocks[b], 0);
+    }
+  }
+  // one member per thread executes a few more non-FP64 instructions per member-step (tableau operands,
+  // loop control and the shared time grid are not amortised over two members)
+  dfb_host::GeometryCandidate cand[6];
+  int nc = 0;
+  const int force_tpt = dfb_host::env_int("DFB_ODE_TPT", 0);
+  const int force_block = dfb_host::env_int("DFB_ODE_BLOCK", 0);
+  for (int tpt = 2; tpt >= 1; --tpt) {
+    if (tpt == 2 && !allow2) continue;
+    if (force_tpt && force_tpt != tpt && !(tpt == 1 && !allow2)) continue;
+    for (int b = 0; b < 3; ++b) {
+      if (force_block && force_block != blocks[b]) continue;
+      cand[nc++] = {blocks[b], tpt, tpt == 2 ? occ2[b] : occ1[b], tpt == 2 ? 1.0 : 1.02};
+    }
+  }
+  if (nc == 0) cand[nc++] = {128, 1, occ1[0], 1.02};
+  return dfb_host::choose_geometry(n, n_sm, cand, nc);
+}
 
 // TRACEABLE: also instantiate the variant that samples the trajectory (Trace output policy); kept to
 // the two tableaux people integrate with (rktp64, rk4) to bound the number of instantiations — a
@@ -28,32 +57,26 @@ bool try_launch(int S_rt, unsigned long long amask, unsigned bmask, const OdeFix
   if ((amask & ~AMASK) != 0ull || (bmask & ~BMASK) != 0u) return false;  // kernel must cover every non-zero
   const bool trace = A.trace_every > 0;
   if (trace && !TRACEABLE) return false;
-  int tpt = default_tpt<Sys, S>();
-  if (const char* e = getenv("DFB_ODE_TPT")) tpt = atoi(e) == 2 ? 2 : 1;
-  if (Sys::N * (S + 3) > 40) tpt = 1;
-  const size_t per_block = size_t(kBlock) * tpt;
-  const size_t grid = (A.n_traj + per_block - 1) / per_block;
-  if (tpt == 2) {
-    if constexpr (Sys::N * (S + 3) <= 40) {
-      if constexpr (TRACEABLE) {
-        if (trace) {
-          ode_fixed_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 2, true><<<unsigned(grid), kBlock, 0, stream>>>(A);
-          *rc = int(cudaGetLastError());
-          return true;
-        }
-      }
-      ode_fixed_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 2><<<unsigned(grid), kBlock, 0, stream>>>(A);
+  constexpr bool kTwo = Sys::N * (S + 3) <= 40;  // the doubled register footprint still fits
+  constexpr int kTpt2 = kTwo ? 2 : 1;
+  if constexpr (TRACEABLE) {
+    if (trace) {
+      const auto g = pick_geometry<ode_fixed_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 1, true>,
+                                   ode_fixed_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, kTpt2, true>>(kTwo, A.n_traj);
+      if (g.tpt == 2)
+        ode_fixed_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, kTpt2, true><<<unsigned(g.grid), g.block, 0, stream>>>(A);
+      else
+        ode_fixed_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 1, true><<<unsigned(g.grid), g.block, 0, stream>>>(A);
+      *rc = int(cudaGetLastError());
+      return true;
     }
-  } else {
-    if constexpr (TRACEABLE) {
-      if (trace) {
-        ode_fixed_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 1, true><<<unsigned(grid), kBlock, 0, stream>>>(A);
-        *rc = int(cudaGetLastError());
-        return true;
-      }
-    }
-    ode_fixed_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 1><<<unsigned(grid), kBlock, 0, stream>>>(A);
   }
+  const auto g = pick_geometry<ode_fixed_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 1>,
+                               ode_fixed_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, kTpt2>>(kTwo, A.n_traj);
+  if (g.tpt == 2)
+    ode_fixed_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, kTpt2><<<unsigned(g.grid), g.block, 0, stream>>>(A);
+  else
+    ode_fixed_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 1><<<unsigned(g.grid), g.block, 0, stream>>>(A);
   *rc = int(cudaGetLastError());
   return true;
 }

@@ -199,6 +199,20 @@ def dde_relay_clamp(arith="strict", t1=100.0):  # examples/dde-relay-clamp.rs:19
             .arith(arith).log_events(EventLog(512)))
 
 
+def dde_relay_clamp_ensemble(n, arith="fast", t1=30.0, events=0, trace=None):
+    # examples/dde-relay-clamp.rs:19-36 as an ensemble over alpha (DDE + propagation + located events)
+    alpha = np.linspace(3.0, 7.0, n)
+    prm = np.stack([alpha, np.full(n, 0.4), np.full(n, 1.0)], axis=1)
+    y0 = np.stack([np.ones(n), -alpha], axis=1)
+    s = (Solver.new().initial(y0).equation(systems.DdeRelayClamp, prm).interval(0.0, t1).stepsize(0.012)
+         .with_const_delay(1.0, 2).on(Locator.zero("abs_delayed_x_minus_1"), None).arith(arith))
+    if events:
+        s = s.log_events(EventLog(events))
+    if trace is not None:
+        s = s.on_step(trace)
+    return s
+
+
 def fibonacci(arith="strict"):  # examples/ode-linear-3-fibonacci.rs:11-25
     a = [-0.21520447048200203, 0.43040894096400406, 3.141592653589793,
          0.43040894096400406, 0.21520447048200203, -1.941611038725466,

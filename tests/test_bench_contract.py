@@ -47,7 +47,7 @@ def test_native_arm_json_line_has_every_contract_key():
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
         assert key in d, key
-    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["scaling"] == "weak"
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["scaling"] == "strong"
     assert d["vs_baseline"] is None and d["dtype"] == "f64" and "workload" in d["config"]
     assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
     assert d["e2e"]["h2d_bytes_per_step"] == 65536 * 6 * 8 and d["e2e"]["d2h_bytes_per_step"] == 65536 * 4 * 8
@@ -65,11 +65,34 @@ def test_dde_leg_report_combines_ranks_and_survives_a_failed_rank():
     import importlib
     bench = importlib.import_module("bench")
     n = bench.DDE_MEMBERS
-    local = {"mean_ms": 18.5, "err": 1e-11, "steps": 5001 * n, "n_failed": 0}
-    rep = bench.dde_report(local, 1, None, None)
+    K = 3
+    local = {"total_ms": 18.5 * K, "e2e_s": 0.020 * K, "err": 1e-11, "steps": 5001 * n, "n_failed": 0,
+             "h2d": n * 40, "d2h": n * 16, "phases": {}, "n_local": n}
+    rep = bench.dde_report(local, None, n, K, "strong")
     assert rep["n_gpus"] == 1 and rep["rk_steps_per_member"] == 5001 and rep["n_failed"] == 0
+    assert rep["members_total"] == n and rep["scaling"] == "strong"
     assert abs(rep["value"] - 5001 * n / 18.5e-3) < 1.0
     rf = rep["roofline"]
     assert rf["bound"] == "hbm" and abs(rf["achieved"] - bench.DDE_BYTES_PER_STEP * rep["value"] / 1e9) < 1e-6
     assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
-    assert bench.dde_report({"error": "boom"}, 1, None, None) == {"error": "boom"}
+    assert abs(rep["e2e"]["value"] - 5001 * n / 0.020) < 1.0 and rep["e2e"]["h2d_bytes_per_step"] == n * 40
+    assert bench.dde_report({"error": "boom"}, None, n, K, "strong") == {"error": "boom"}
+
+
+def test_shards_of_the_strong_scaling_run_tile_the_baseline_ensemble():
+    sys.path.insert(0, ROOT)
+    import importlib
+    import numpy as np
+    bench = importlib.import_module("bench")
+    total = 1000
+    y_all, p_all = bench.lorenz_inputs(total, 0, total)
+    for world in (1, 2, 3, 8):
+        rows = []
+        for r in range(world):
+            lo, hi = bench.shard_bounds(total, r, world)
+            rows.append(bench.lorenz_inputs(total, lo, hi)[1])
+        assert np.array_equal(np.concatenate(rows), p_all)
+    # both arms print the same config dict (the driver compares them)
+    assert bench.make_config("strong", 8) == bench.make_config("strong", 8, "fast")
+    assert bench.make_config("strong", 8)["members_total"] == bench.N_MEMBERS
+    assert bench.make_config("weak", 8)["members_total"] == 8 * bench.N_MEMBERS

@@ -6,6 +6,8 @@ random inputs are unlikely to share a misreading; the oracle is the checker of e
 import json
 import os
 
+import zlib
+
 import numpy as np
 import pytest
 
@@ -66,7 +68,7 @@ SYSTEMS = {
 
 @pytest.mark.parametrize("rk_name", sorted(TABLEAUX))
 def test_oracle_equals_independent_numpy_restatement(oracle, rk_name):
-    rng = np.random.default_rng(abs(hash(rk_name)) % (2 ** 31))
+    rng = np.random.default_rng(zlib.crc32(rk_name.encode()))  # str hashes are salted per process
     tab = tableau(rk_name)
     for sys_name, (system, N, NP, make_rhs) in SYSTEMS.items():
         n = 3
@@ -84,4 +86,4 @@ def test_oracle_equals_independent_numpy_restatement(oracle, rk_name):
             t, p, steps, evals = run_numpy(make_rhs(prm[i] if prm is not None else None), y0[i], t0, t1, h, tab)
             assert o.steps[i] == steps and o.rhs_evals[i] == evals, (rk_name, sys_name)
             assert o.t[i] == t, (rk_name, sys_name)
-            assert np.array_equal(o.p[i], p), (rk_name, sys_name, o.p[i], p)
+            assert np.array_equal(o.p[i], p, equal_nan=True), (rk_name, sys_name, o.p[i], p)

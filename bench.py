@@ -171,7 +171,7 @@ def cpu_oracle_rate_dde(n_sample, threads):
 
 
 def sized_cpu_baseline(rate_fn, steps_per_member, cores, seconds, label):
-    probe_rate, _, _ = rate_fn(16 * cores, cores)  # sizes the sample for ~`seconds` of CPU work
+    probe_rate, _, _ = rate_fn(128 * cores, cores)  # sizes the sample for ~`seconds` of CPU work
     n_sample = int(max(32 * cores, seconds * probe_rate / steps_per_member))
     n_sample -= n_sample % cores
     rate, dt, _ = rate_fn(n_sample, cores)
@@ -477,7 +477,15 @@ def other_config_legs(d, peak_tflops):
             d.systems.NddeLinear, *[x.ravel() for x in np.meshgrid(np.linspace(-2.0, 0.5, 256), np.linspace(-0.6, 0.6, 256))])[0], None, 0.0),
         # DDE + located events (examples/dde-relay-clamp.rs), sigma sweep
         "dde_relay_clamp_2^16_alpha_sweep_t=[0,30]": (lambda: cases.dde_relay_clamp_ensemble(1 << 16, arith="fast"), None, 0.0),
+        "dde_relay_clamp_2^18_alpha_sweep_t=[0,30]": (lambda: cases.dde_relay_clamp_ensemble(1 << 18, arith="fast"), None, 0.0),
     }
+    # dde_event_kernel: one coefficient record (t, y[N], d_1..d_4[N]) = 8 (1 + N I) B written and one read per
+    # committed step (N = 2, I = 5: 88 B each)
+    hbm_bytes_per_step = {"dde_relay_clamp_2^16_alpha_sweep_t=[0,30]": 176.0, "dde_relay_clamp_2^18_alpha_sweep_t=[0,30]": 176.0}
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        hbm_peak = 6650.0
     for name, (mk, flops, iter_flops) in legs.items():
         try:
             r = timed(mk)
@@ -491,6 +499,12 @@ def other_config_legs(d, peak_tflops):
                     total_flops += iter_flops * r["locate_iters"]
                 r["achieved_tflops"] = total_flops / (r["kernel_ms"] * 1e-3) / 1e12
                 r["frac_of_fp64_peak"] = r["achieved_tflops"] / peak_tflops
+            if name in hbm_bytes_per_step:
+                r["algorithmic_hbm_bytes_per_step"] = hbm_bytes_per_step[name]
+                r["achieved_gbs"] = hbm_bytes_per_step[name] * r["rk_steps"] / (r["kernel_ms"] * 1e-3) / 1e9
+                r["frac_of_hbm_peak"] = r["achieved_gbs"] / hbm_peak
+                if r.get("locate_iters"):
+                    r["mean_bisection_iters_per_event"] = r["locate_iters"] / max(r["events"], 1)
             out[name] = r
         except Exception as e:  # the headline line must still print
             out[name] = {"error": repr(e)}

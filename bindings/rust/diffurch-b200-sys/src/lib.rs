@@ -4,7 +4,7 @@
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const DFB_ABI_VERSION: i32 = 2;
+pub const DFB_ABI_VERSION: i32 = 3;
 pub const DFB_MAX_STAGES: usize = 7;
 pub const DFB_MAX_INTERP: usize = 5;
 pub const DFB_MAX_STATE: usize = 12;
@@ -127,6 +127,7 @@ pub struct dfb_totals {
     pub kernel_ms: f64,
     pub kernel_launches: u32,
     pub kernel_kind: u32,
+    pub locate_iters: u64,
 }
 
 #[repr(C)]

@@ -6,7 +6,7 @@ compiled library reports.
 """
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_STAGES = 7
 MAX_INTERP = 5
 MAX_STATE = 12
@@ -31,7 +31,7 @@ TRAJ_DISCO_OVERFLOW = 128
 TRAJ_STEPSIZE_FLOOR = 256
 # dfb_kernel_kind (dfb_totals.kernel_kind)
 KERNEL_GENERAL, KERNEL_ODE_FIXED, KERNEL_DDE_FIXED, KERNEL_ODE_ADAPTIVE = 0, 1, 2, 3
-KERNEL_ODE_FIXED_PERIODIC, KERNEL_ODE_EVENT = 4, 5
+KERNEL_ODE_FIXED_PERIODIC, KERNEL_ODE_EVENT, KERNEL_DDE_EVENT = 4, 5, 6
 
 # dfb_system_id
 SYS_LORENZ = 1
@@ -155,6 +155,7 @@ class Totals(C.Structure):
         ("rhs_evals", C.c_uint64), ("n_failed", C.c_uint64),
         ("kernel_ms", C.c_double),
         ("kernel_launches", C.c_uint32), ("kernel_kind", C.c_uint32),
+        ("locate_iters", C.c_uint64),
     ]
 
 

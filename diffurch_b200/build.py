@@ -30,6 +30,7 @@ def _jobs():
             jobs.append(("kernels_general.cu", f"general_g{g}_{tag}.o",
                          [f"-DDFB_ARITH={arith}", f"-DDFB_GROUP={g}"] + extra))
     jobs.append(("kernels_dde_fixed.cu", "dde_fixed_fast.o", ["-DDFB_ARITH=1"]))
+    jobs.append(("kernels_dde_event.cu", "dde_event_fast.o", ["-DDFB_ARITH=1"]))
     jobs.append(("kernels_ode_adaptive.cu", "ode_adaptive_fast.o", ["-DDFB_ARITH=1"]))
     jobs.append(("api.cu", "api.o", []))
     return jobs

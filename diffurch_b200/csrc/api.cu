@@ -35,6 +35,17 @@ int run_dde_fixed_shim(int system_id, const dfb_tableau& rk, double t0, double t
                        uint32_t* status, int trace_every, int trace_capacity, double* trace_t,
                        double* trace_y, uint32_t* n_samples, cudaStream_t stream);
 size_t dde_fixed_ring_doubles(int n_state, int I, int capacity);
+int run_dde_event_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h, double max_delay,
+                       long long max_steps, int history_id, int ring_capacity, unsigned ring_warps, double* ring,
+                       size_t n, const double* y0, const double* params, double* t_final, double* y_final,
+                       double* aux_final, unsigned long long* steps, unsigned long long* events,
+                       unsigned long long* rhs_evals, unsigned long long* locate_iters, uint32_t* status,
+                       int n_loc, const dfb_locator* loc, int n_disco, const double* disco_t,
+                       const int32_t* disco_order, int event_capacity, double* ev_t, int32_t* ev_idx,
+                       uint32_t* n_events, int trace_every, int trace_capacity, double* trace_t, double* trace_y,
+                       uint32_t* n_samples, unsigned long long* queue, int locate_batch, int locate_wait, int n_sm,
+                       int on_start_cb, cudaStream_t stream);
+int dde_event_query(int system_id, int S, int I);
 int run_ode_adaptive_shim(int system_id, const dfb_tableau& rk, const dfb_auto_stepsize& ctl, double t0,
                           double t1, size_t n, const double* y0, const double* params, double* t_final,
                           double* y_final, unsigned long long* steps, unsigned long long* rejected,
@@ -67,12 +78,13 @@ const DfbLaunchTable kBuiltinFast = {
     dfb_fast::run_ode_fixed_shim, dfb_fast::run_ode_fixed_periodic_shim, dfb_fast::run_ode_event_shim,
     dfb_fast::run_ode_adaptive_shim, dfb_fast::run_dde_fixed_shim,
     {dfb_fast::launch_general_g1, dfb_fast::launch_general_g2, dfb_fast::launch_general_g3,
-     dfb_fast::launch_general_g4, dfb_fast::launch_general_g5}, 5};
+     dfb_fast::launch_general_g4, dfb_fast::launch_general_g5}, 5,
+    dfb_fast::run_dde_event_shim, dfb_fast::dde_event_query};
 const DfbLaunchTable kBuiltinStrict = {
     dfb_strict::run_ode_fixed_shim, dfb_strict::run_ode_fixed_periodic_shim, dfb_strict::run_ode_event_shim,
     nullptr, nullptr,
     {dfb_strict::launch_general_g1, dfb_strict::launch_general_g2, dfb_strict::launch_general_g3,
-     dfb_strict::launch_general_g4, dfb_strict::launch_general_g5}, 5};
+     dfb_strict::launch_general_g4, dfb_strict::launch_general_g5}, 5, nullptr, nullptr};
 
 struct PluginSys {
   SysInfo info;
@@ -199,6 +211,10 @@ struct dfb_handle {
   double *d_ring_t = nullptr, *d_ring_y = nullptr, *d_ring_k = nullptr;
   double* d_ring_coeff = nullptr;  // coefficient-record ring of the DDE hot-path kernel
   bool dde_hot = false;
+  double* d_ring_event = nullptr;  // per-lane coefficient ring of dde_event_kernel ([cap][warps][1 + N I][32])
+  unsigned ring_event_warps = 0;
+  bool dde_event = false;
+  unsigned long long* d_locate_iters = nullptr;
   double* d_disco_t = nullptr;
   int32_t* d_disco_ord = nullptr;
   unsigned long long* d_queue = nullptr;  // work counter of the dynamically scheduled kernels
@@ -224,7 +240,8 @@ void free_all(dfb_handle* h) {
                   h->d_aux,     h->d_steps,   h->d_rejected, h->d_events,  h->d_rhs,
                   h->d_status,  h->d_trace_t, h->d_trace_y,  h->d_nsamples, h->d_ev_t,
                   h->d_ev_idx,  h->d_nevents, h->d_ring_t,   h->d_ring_y,  h->d_ring_k,
-                  h->d_disco_t, h->d_disco_ord, h->d_ring_coeff, h->d_queue};
+                  h->d_disco_t, h->d_disco_ord, h->d_ring_coeff, h->d_queue, h->d_ring_event,
+                  h->d_locate_iters};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -318,6 +335,31 @@ int launch_general(dfb_handle* h, const DevProblem& P, cudaStream_t stream) {
   }
   return fail(DFB_ERR_UNSUPPORTED,
               "no compiled kernel for this (system, tableau shape): see kernels_general.cu");
+}
+
+// History rings of the general kernel (reference record format: t, y, k[S]).
+int alloc_general_rings(dfb_handle* h) {
+  if (h->d_ring_t) return DFB_OK;
+  const dfb_problem* desc = &h->prob;
+  const size_t n = h->n;
+  const int N = h->info.n_state, S = desc->rk.S;
+  size_t cap = size_t(desc->ring_capacity);
+  if (cap == 0) {
+    // window of the reference's deque: ceil(max_delay / h) + 3 records, plus two
+    // per located event inside the window (solver.rs:304,308); doubled for slack.
+    double hmin = desc->stepsize_kind == DFB_STEP_AUTOMATIC ? desc->automatic.stepsize_min : desc->h;
+    double want = std::isfinite(desc->max_delay) && hmin > 0 ? std::ceil(desc->max_delay / hmin) : 1024.0;
+    if (!(want < 1e6)) want = 1e6;
+    cap = size_t(want) * 2 + 16;
+  }
+  cap = next_pow2(cap);
+  if (cap > (1u << 20)) return fail(DFB_ERR_INVALID, "history ring capacity too large; set ring_capacity explicitly");
+  h->ring_capacity = int(cap);
+  cudaError_t e = dalloc(&h->d_ring_t, n * cap);
+  if (e == cudaSuccess) e = dalloc(&h->d_ring_y, n * cap * N);
+  if (e == cudaSuccess) e = dalloc(&h->d_ring_k, n * cap * N * S);
+  if (e != cudaSuccess) return fail(DFB_ERR_CUDA, std::string("cudaMalloc history rings: ") + cudaGetErrorString(e));
+  return DFB_OK;
 }
 
 }  // namespace
@@ -463,10 +505,7 @@ int dfb_create(const dfb_problem* desc, size_t n_traj, int device, dfb_handle** 
   H_ALLOC(h->d_steps, n);
   H_ALLOC(h->d_rejected, n);
   H_ALLOC(h->d_queue, 1);
-  {
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->n_sm = prop.multiProcessorCount;
-  }
+  cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
   H_ALLOC(h->d_events, n);
   H_ALLOC(h->d_rhs, n);
   H_ALLOC(h->d_status, n);
@@ -492,41 +531,73 @@ int dfb_create(const dfb_problem* desc, size_t n_traj, int device, dfb_handle** 
                  dde_hot_system(desc->system_id) && table_for(desc->system_id, DFB_ARITH_FAST).dde_fixed &&
                  std::isfinite(desc->max_delay) && desc->max_delay > 0.0 &&
                  desc->max_delay / desc->h < 60000.0 && !std::getenv("DFB_FORCE_GENERAL");
-    if (h->dde_hot) {  // the kernel indexes the ring with 32-bit offsets and counts steps in an int
-      const double cap_est = double(next_pow2(size_t(std::ceil(desc->max_delay / desc->h)) + 8));
+    // what run_dde_fixed_shim requires of the tableau (checked here so that an unsupported one gets the
+    // general rings and the general kernel): b_i(0) = 0, and no stage after the first at the step start
+    for (int i = 0; i < S_ && h->dde_hot; ++i) {
+      if (desc->rk.bi[i * DFB_MAX_INTERP] != 0.0) h->dde_hot = false;
+      if (i >= 1 && !(desc->rk.c[i] * desc->h > 0.0)) h->dde_hot = false;
+    }
+    if (h->dde_hot) {
+      // records the reference's deque can hold: ceil(max_delay / h) + 3; + window/prefetch slack.  A
+      // caller-supplied capacity below that would let the ring wrap over records the streaming window
+      // still reads (the kernel has no overflow check), so it is only ever rounded UP.
+      size_t cap = size_t(std::ceil(desc->max_delay / desc->h)) + 8;
+      if (size_t(desc->ring_capacity) > cap) cap = size_t(desc->ring_capacity);
+      cap = next_pow2(cap);
+      // the kernel indexes the ring with 32-bit offsets and counts steps in an int: guard the capacity
+      // actually used
       const double steps_est = (desc->t1 - desc->t0) / desc->h;
-      if (cap_est * double((n + 31) / 32 * 32) * double(2 + N * desc->rk.I) >= 4.0e9 || !(steps_est < 2.0e9))
+      if (double(cap) * double((n + 31) / 32 * 32) * double(N * desc->rk.I) >= 4.0e9 || !(steps_est < 2.0e9))
         h->dde_hot = false;
+      else
+        h->ring_capacity = int(cap);
+    }
+  }
+  // DDE / NDDE + located events + propagation hot path (dev/dde_event.cuh): FAST arithmetic, fixed step.
+  if (!h->dde_hot) {
+    const DfbLaunchTable& TF = table_for(desc->system_id, DFB_ARITH_FAST);
+    bool ok = desc->arith == DFB_ARITH_FAST && desc->stepsize_kind == DFB_STEP_FIXED &&
+              (info->uses_history || h->uses_disco) && !h->ode_history && TF.dde_event && TF.dde_event_query &&
+              TF.dde_event_query(desc->system_id, desc->rk.S, desc->rk.I) == 1 && !std::getenv("DFB_FORCE_GENERAL");
+    for (int i = 0; i < desc->rk.S && ok; ++i)
+      if (desc->rk.bi[i * DFB_MAX_INTERP] != 0.0) ok = false;  // pre-combined records need b_i(0) = 0
+    for (int l = 0; l < desc->n_loc && ok; ++l)
+      ok = desc->loc[l].kind == DFB_LOC_STATEFN || desc->loc[l].kind == DFB_LOC_PERIODIC ||
+           desc->loc[l].kind == DFB_LOC_PROPAGATION;
+    if (ok) {
+      size_t cap = size_t(desc->ring_capacity);
+      if (cap == 0) {  // as for the general rings below
+        double want = std::isfinite(desc->max_delay) && desc->h > 0 ? std::ceil(desc->max_delay / desc->h) : 1024.0;
+        if (!(want < 1e6)) want = 1e6;
+        cap = size_t(want) * 2 + 16;
+      }
+      cap = next_pow2(cap);
+      // one ring column per resident thread (members are assigned dynamically): never more than the
+      // device can hold resident, never more than the ensemble
+      size_t lanes = (n + 127) / 128 * 128;  // whole 128-thread blocks
+      const size_t resident_max = size_t(h->n_sm > 0 ? h->n_sm : 148) * 2048;
+      if (lanes > resident_max) lanes = resident_max;
+      const size_t rec = size_t(1 + N * desc->rk.I);
+      if (cap <= (1u << 20) && double(cap) * double(lanes) * double(rec) < 4.0e9) {
+        h->dde_event = true;
+        h->ring_capacity = int(cap);
+        h->ring_event_warps = unsigned(lanes / 32);
+      }
     }
   }
   if (h->dde_hot) {
-    // records the reference's deque can hold: ceil(max_delay / h) + 3; + window/prefetch slack
-    size_t cap = size_t(desc->ring_capacity);
-    if (cap == 0) cap = size_t(std::ceil(desc->max_delay / desc->h)) + 8;
-    cap = next_pow2(cap);
-    h->ring_capacity = int(cap);
-    H_ALLOC(h->d_ring_coeff, ((n + 31) / 32 * 32) * dfb_fast::dde_fixed_ring_doubles(N, desc->rk.I, int(cap)));
+    H_ALLOC(h->d_ring_coeff, ((n + 31) / 32 * 32) * dfb_fast::dde_fixed_ring_doubles(N, desc->rk.I, h->ring_capacity));
+  } else if (h->dde_event) {
+    H_ALLOC(h->d_ring_event, size_t(h->ring_capacity) * size_t(h->ring_event_warps) * 32 * size_t(1 + N * desc->rk.I));
   } else if (info->uses_history || h->ode_history) {
-    size_t cap = size_t(desc->ring_capacity);
-    if (cap == 0) {
-      // window of the reference's deque: ceil(max_delay / h) + 3 records, plus two
-      // per located event inside the window (solver.rs:304,308); doubled for slack.
-      double hmin = desc->stepsize_kind == DFB_STEP_AUTOMATIC ? desc->automatic.stepsize_min : desc->h;
-      double want = std::isfinite(desc->max_delay) && hmin > 0 ? std::ceil(desc->max_delay / hmin) : 1024.0;
-      if (!(want < 1e6)) want = 1e6;
-      cap = size_t(want) * 2 + 16;
-    }
-    cap = next_pow2(cap);
-    if (cap > (1u << 20)) {
+    const int rc_rings = alloc_general_rings(h);
+    if (rc_rings != DFB_OK) {
       free_all(h);
       delete h;
-      return fail(DFB_ERR_INVALID, "history ring capacity too large; set ring_capacity explicitly");
+      return rc_rings;
     }
-    h->ring_capacity = int(cap);
-    H_ALLOC(h->d_ring_t, n * cap);
-    H_ALLOC(h->d_ring_y, n * cap * N);
-    H_ALLOC(h->d_ring_k, n * cap * N * S);
   }
+  if (desc->n_loc > 0) H_ALLOC(h->d_locate_iters, n);
   if (h->uses_disco) {
     H_ALLOC(h->d_disco_t, n * DFB_DISCO_CAP);
     H_ALLOC(h->d_disco_ord, n * DFB_DISCO_CAP);
@@ -602,6 +673,7 @@ int dfb_run(dfb_handle* h, void* stream_v) {
   const double* params = h->d_params_ext ? h->d_params_ext : h->d_params;
   h->launches = 0;
   const DfbLaunchTable& T = table_for(p.system_id, p.arith);
+  if (h->d_locate_iters) DFB_CUDA(cudaMemsetAsync(h->d_locate_iters, 0, n * sizeof(unsigned long long), stream));
 
   // Hot path: fixed step, no locators, no history, final state only.
   const bool no_start_cb = p.on_start_callback_id == DFB_CB_NONE;
@@ -666,7 +738,8 @@ int dfb_run(dfb_handle* h, void* stream_v) {
     const DfbOdeEventFn shim = T.ode_event;
     const bool tracing = h->d_trace_t && p.trace_every > 0;
     const int rc = !shim ? -1 : shim(p.system_id, p.rk, p.t0, p.t1, p.h, p.max_steps, n, y0, params, h->d_t, h->d_y,
-                        h->info.n_aux ? h->d_aux : nullptr, h->d_steps, h->d_events, h->d_rhs, h->d_status,
+                        h->info.n_aux ? h->d_aux : nullptr, h->d_steps, h->d_events, h->d_rhs, h->d_locate_iters,
+                        h->d_status,
                         p.n_loc, p.loc, p.event_capacity, h->d_ev_t, h->d_ev_idx, h->d_nevents,
                         tracing ? p.trace_every : 0, p.trace_capacity, tracing ? h->d_trace_t : nullptr,
                         h->d_trace_y, h->d_nsamples, h->d_queue, h->locate_batch, h->locate_max_wait, h->n_sm,
@@ -719,14 +792,44 @@ int dfb_run(dfb_handle* h, void* stream_v) {
                                                 h->d_status, dde_tracing ? p.trace_every : 0, p.trace_capacity,
                                                 dde_tracing ? h->d_trace_t : nullptr, h->d_trace_y, h->d_nsamples, stream);
     if (rc > 0) return fail(DFB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(cudaError_t(rc)));
-    if (rc < 0) return fail(DFB_ERR_UNSUPPORTED, "no DDE hot-path kernel for this tableau");
-    DFB_CUDA(cudaEventRecord(h->ev1, stream));
-    h->launches = 1;
-    h->kernel_kind = DFB_KERNEL_DDE_FIXED;
-    h->ran = true;
-    return DFB_OK;
+    if (rc == 0) {
+      DFB_CUDA(cudaEventRecord(h->ev1, stream));
+      h->launches = 1;
+      h->kernel_kind = DFB_KERNEL_DDE_FIXED;
+      h->ran = true;
+      return DFB_OK;
+    }
+    // rc == -1: no specialised kernel after all -> general path below (its rings are allocated on demand)
   }
 
+  // DDE / NDDE + located events + propagation (dev/dde_event.cuh), FAST arithmetic.
+  if (h->dde_event && T.dde_event) {
+    DFB_CUDA(cudaMemsetAsync(h->d_rejected, 0, n * sizeof(unsigned long long), stream));
+    DFB_CUDA(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned long long), stream));
+    DFB_CUDA(cudaEventRecord(h->ev0, stream));
+    const bool tracing = h->d_trace_t && p.trace_every > 0;
+    const int rc = T.dde_event(p.system_id, p.rk, p.t0, p.t1, p.h, p.max_delay, p.max_steps, p.history_id,
+                               h->ring_capacity, h->ring_event_warps, h->d_ring_event, n, y0, params, h->d_t,
+                               h->d_y, h->info.n_aux ? h->d_aux : nullptr, h->d_steps, h->d_events, h->d_rhs,
+                               h->d_locate_iters, h->d_status, p.n_loc, p.loc, p.n_disco, p.disco_t, p.disco_order,
+                               p.event_capacity, h->d_ev_t, h->d_ev_idx, h->d_nevents, tracing ? p.trace_every : 0,
+                               p.trace_capacity, tracing ? h->d_trace_t : nullptr, h->d_trace_y, h->d_nsamples,
+                               h->d_queue, h->locate_batch, h->locate_max_wait, h->n_sm, p.on_start_callback_id,
+                               stream);
+    if (rc > 0) return fail(DFB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(cudaError_t(rc)));
+    if (rc == 0) {
+      DFB_CUDA(cudaEventRecord(h->ev1, stream));
+      h->launches = 1;
+      h->kernel_kind = DFB_KERNEL_DDE_EVENT;
+      h->ran = true;
+      return DFB_OK;
+    }
+  }
+
+  if ((h->info.uses_history || h->ode_history) && !h->d_ring_t) {
+    const int rc_rings = alloc_general_rings(h);
+    if (rc_rings != DFB_OK) return rc_rings;
+  }
   DevProblem P;
   std::memset(&P, 0, sizeof(P));
   P.rk = p.rk;
@@ -856,6 +959,10 @@ int dfb_get_totals(dfb_handle* h, dfb_totals* out) {
     out->events += c[i];
     out->rhs_evals += d[i];
     if (st[i] & ~uint32_t(DFB_TRAJ_STOPPED)) out->n_failed++;
+  }
+  if (h->d_locate_iters && (h->kernel_kind == DFB_KERNEL_ODE_EVENT || h->kernel_kind == DFB_KERNEL_DDE_EVENT)) {
+    DFB_CUDA(cudaMemcpy(a.data(), h->d_locate_iters, n * 8, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) out->locate_iters += a[i];
   }
   float ms = 0.f;
   DFB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));

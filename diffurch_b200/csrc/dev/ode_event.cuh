@@ -78,6 +78,7 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
   bool combined;  // k[1 .. I-1] of the step in flight already hold the interpolant coefficients
   unsigned n_steps, n_events, n_evlog, n_samples;
   unsigned long long n_rhs, on_step_calls;
+  unsigned n_iters;  // location-loop iterations of this member (dfb_totals.locate_iters)
 
   __device__ explicit OdeEventStepper(const OdeFixedArgs& A_) : Base(A_) {}
 
@@ -199,6 +200,7 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
         else rgt = m;
         m = 0.5 * (lft + rgt);
         w = fabs(rgt - lft);
+        ++n_iters;
       }
       return fmax(lft, rgt);
     }
@@ -232,6 +234,7 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
         if (fv[2] < 0.0) rgt = m;
         else lft = m;
         w = fabs(rgt - lft);
+        ++n_iters;
       }
       return fmax(lft, rgt);
     }
@@ -246,6 +249,7 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
       else rgt = m;
       m = 0.5 * (lft + rgt);
       w = fabs(rgt - lft);
+      ++n_iters;
     }
     return fmax(lft, rgt);
   }
@@ -349,7 +353,7 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
       every_i[l] = on_times ? 0 : (l < A.n_loc ? A.loc[l].filter_n - 1 : 0);
       sep_prev[l] = on_times ? 0.0 : -1.7976931348623157e308;  // T::min_value() / list position
     }
-    n_steps = n_events = n_evlog = n_samples = 0u;
+    n_steps = n_events = n_evlog = n_samples = n_iters = 0u;
     n_rhs = on_step_calls = 0ull;
     if (A.on_start_cb != DFB_CB_NONE) {  // events_on_start.eval_mut (solver.rs:289)
       RefMut m{&t_curr, p_curr(), d_curr(), t_prev, p_prev(), &this->nohist};
@@ -378,6 +382,7 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
     A.events[gid] = n_events;
     A.rhs_evals[gid] = n_rhs;
     A.status[gid] = st;
+    if (A.locate_iters) A.locate_iters[gid] = n_iters;
     if (A.n_events) A.n_events[gid] = n_evlog;
     if (A.n_samples) A.n_samples[gid] = n_samples;
   }

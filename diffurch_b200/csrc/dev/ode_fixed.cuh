@@ -52,6 +52,7 @@ struct OdeFixedArgs {
   double bi[DFB_MAX_STAGES * DFB_MAX_INTERP];  // continuous extension (rk.rs:13)
   long long max_steps;
   unsigned long long* queue;     // work counter (zeroed before the launch)
+  unsigned long long* locate_iters;  // [n] location-loop iterations per member (may be null)
   int32_t locate_batch, locate_wait;
   int32_t inner_steps;           // step rounds between two warp votes (>= 1)
   int32_t on_start_cb;           // Solver::on_start_mut: callback id run on the initial State (0 = none)

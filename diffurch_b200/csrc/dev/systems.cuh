@@ -139,6 +139,10 @@ struct SysBase {
   // the system has exactly one constant delay and says so with `const_delay(prm)`: lets the
   // coefficient-ring DDE kernel (dev/dde_fixed.cuh) take it
   static constexpr bool has_const_delay = false;
+  // every detector is a pure function of the view's (t, p, d) and of the history p(.) / d(.): it reads
+  // neither t_prev nor p_prev.  Lets dde_event_kernel reuse a detector's value at a step end as the
+  // next step's eval_prev instead of evaluating it again (state_fn.rs:181-188)
+  static constexpr bool pure_detectors = false;
   template <class V>
   __device__ static double detector(int, const V&, const double*) { return 0.0; }
   template <class M>
@@ -383,6 +387,7 @@ struct SysDdeRelayClamp : SysBase {  // examples/dde-relay-clamp.rs:24-35
   static constexpr int ID = DFB_SYS_DDE_RELAY_CLAMP, N = 2, NP = 3, ND = 1;
   static constexpr bool uses_history = true;
   static constexpr bool pure_rhs = false;
+  static constexpr bool pure_detectors = true;
   template <class V>
   __device__ __forceinline__ static void rhs(const V& s, const double* prm, double* out) {
     const double x = s.p[0], dx = s.p[1];

@@ -89,7 +89,8 @@ int launch_ode_event(int system_id, int S, int I, const OdeFixedArgs& A, int n_s
 int run_ode_event_shim(int system_id, const dfb_tableau& rk, double t0, double t1, double h, long long max_steps,
                        size_t n, const double* y0, const double* params, double* t_final, double* y_final,
                        double* aux_final, unsigned long long* steps, unsigned long long* events,
-                       unsigned long long* rhs_evals, uint32_t* status, int n_loc, const dfb_locator* loc,
+                       unsigned long long* rhs_evals, unsigned long long* locate_iters, uint32_t* status,
+                       int n_loc, const dfb_locator* loc,
                        int event_capacity, double* ev_t, int32_t* ev_idx, uint32_t* n_events, int trace_every,
                        int trace_capacity, double* trace_t, double* trace_y, uint32_t* n_samples,
                        unsigned long long* queue, int locate_batch, int locate_wait, int n_sm,
@@ -119,6 +120,7 @@ int run_ode_event_shim(int system_id, const dfb_tableau& rk, double t0, double t
   A.steps = steps;
   A.events = events;
   A.rhs_evals = rhs_evals;
+  A.locate_iters = locate_iters;
   A.status = status;
   A.n_loc = n_loc;
   for (int l = 0; l < n_loc && l < DFB_MAX_LOCATORS; ++l) A.loc[l] = loc[l];

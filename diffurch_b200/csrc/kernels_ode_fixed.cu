@@ -40,10 +40,10 @@ dfb_host::LaunchGeometry pick_geometry(bool allow2, size_t n) {
     if (force_tpt && force_tpt != tpt && !(tpt == 1 && !allow2)) continue;
     for (int b = 0; b < 3; ++b) {
       if (force_block && force_block != blocks[b]) continue;
-      cand[nc++] = {blocks[b], tpt, tpt == 2 ? occ2[b] : occ1[b], tpt == 2 ? 1.0 : 1.02};
+      cand[nc++] = {blocks[b], tpt, tpt == 2 ? occ2[b] : occ1[b], tpt == 2 ? 1.0 : 1.012};
     }
   }
-  if (nc == 0) cand[nc++] = {128, 1, occ1[0], 1.02};
+  if (nc == 0) cand[nc++] = {128, 1, occ1[0], 1.012};
   return dfb_host::choose_geometry(n, n_sm, cand, nc);
 }
 

@@ -20,7 +20,8 @@ typedef int (*DfbOdePeriodicFn)(int system_id, const dfb_tableau& rk, double t0,
 typedef int (*DfbOdeEventFn)(int system_id, const dfb_tableau& rk, double t0, double t1, double h,
                              long long max_steps, size_t n, const double* y0, const double* params,
                              double* t_final, double* y_final, double* aux_final, unsigned long long* steps,
-                             unsigned long long* events, unsigned long long* rhs_evals, uint32_t* status,
+                             unsigned long long* events, unsigned long long* rhs_evals,
+                             unsigned long long* locate_iters, uint32_t* status,
                              int n_loc, const dfb_locator* loc, int event_capacity, double* ev_t,
                              int32_t* ev_idx, uint32_t* n_events, int trace_every, int trace_capacity,
                              double* trace_t, double* trace_y, uint32_t* n_samples, unsigned long long* queue,
@@ -37,6 +38,17 @@ typedef int (*DfbDdeFixedFn)(int system_id, const dfb_tableau& rk, double t0, do
                              unsigned long long* steps, unsigned long long* rhs_evals, uint32_t* status,
                              int trace_every, int trace_capacity, double* trace_t, double* trace_y,
                              uint32_t* n_samples, cudaStream_t stream);
+typedef int (*DfbDdeEventFn)(int system_id, const dfb_tableau& rk, double t0, double t1, double h, double max_delay,
+                             long long max_steps, int history_id, int ring_capacity, unsigned ring_warps,
+                             double* ring, size_t n, const double* y0, const double* params, double* t_final,
+                             double* y_final, double* aux_final, unsigned long long* steps,
+                             unsigned long long* events, unsigned long long* rhs_evals,
+                             unsigned long long* locate_iters, uint32_t* status, int n_loc, const dfb_locator* loc,
+                             int n_disco, const double* disco_t, const int32_t* disco_order, int event_capacity,
+                             double* ev_t, int32_t* ev_idx, uint32_t* n_events, int trace_every,
+                             int trace_capacity, double* trace_t, double* trace_y, uint32_t* n_samples,
+                             unsigned long long* queue, int locate_batch, int locate_wait, int n_sm,
+                             int on_start_cb, cudaStream_t stream);
 typedef int (*DfbGeneralFn)(const DevProblem& P, int system_id, bool has_loc, const LaunchCfg& c,
                             int locate_batch_threshold);
 
@@ -52,6 +64,8 @@ struct DfbLaunchTable {
   DfbDdeFixedFn dde_fixed;
   DfbGeneralFn general[DFB_MAX_GENERAL_GROUPS];
   int n_general;
+  DfbDdeEventFn dde_event;  // FAST only
+  int (*dde_event_query)(int system_id, int S, int I);
 };
 
 #define DFB_DECLARE_SHIMS(NS)                                                                        \
@@ -66,14 +80,15 @@ struct DfbLaunchTable {
                                   uint32_t*, cudaStream_t);                                          \
   int run_ode_event_shim(int, const dfb_tableau&, double, double, double, long long, size_t,        \
                          const double*, const double*, double*, double*, double*,                   \
-                         unsigned long long*, unsigned long long*, unsigned long long*, uint32_t*,  \
+                         unsigned long long*, unsigned long long*, unsigned long long*,             \
+                         unsigned long long*, uint32_t*,                                            \
                          int, const dfb_locator*, int, double*, int32_t*, uint32_t*, int, int,      \
                          double*, double*, uint32_t*, unsigned long long*, int, int, int, int,      \
                          cudaStream_t);                                                              \
   }
 
 // What a plugin's `dfb_plugin_describe` fills in (csrc/plugin_entry.cu).
-#define DFB_PLUGIN_ABI 6
+#define DFB_PLUGIN_ABI 7
 struct dfb_plugin_desc {
   int plugin_abi;
   int n_state, n_params, n_aux, n_detectors, n_callbacks, uses_history;

@@ -16,6 +16,13 @@ namespace dfb_fast {
 int run_dde_fixed_shim(int, const dfb_tableau&, double, double, double, double, int, int, size_t, const double*,
                        const double*, double*, double*, double*, unsigned long long*, unsigned long long*,
                        uint32_t*, int, int, double*, double*, uint32_t*, cudaStream_t);
+int run_dde_event_shim(int, const dfb_tableau&, double, double, double, double, long long, int, int, unsigned,
+                       double*, size_t, const double*, const double*, double*, double*, double*,
+                       unsigned long long*, unsigned long long*, unsigned long long*, unsigned long long*,
+                       uint32_t*, int, const dfb_locator*, int, const double*, const int32_t*, int, double*,
+                       int32_t*, uint32_t*, int, int, double*, double*, uint32_t*, unsigned long long*, int, int,
+                       int, int, cudaStream_t);
+int dde_event_query(int, int, int);
 int run_ode_adaptive_shim(int, const dfb_tableau&, const dfb_auto_stepsize&, double, double, size_t,
                           const double*, const double*, double*, double*, unsigned long long*,
                           unsigned long long*, unsigned long long*, uint32_t*, unsigned long long*, int,
@@ -45,9 +52,10 @@ extern "C" __attribute__((visibility("default"))) int dfb_plugin_describe(dfb_pl
   out->name = DFB_STR(DFB_PLUGIN_SYSTEM);
   out->fast = DfbLaunchTable{dfb_fast::run_ode_fixed_shim, dfb_fast::run_ode_fixed_periodic_shim,
                              dfb_fast::run_ode_event_shim, dfb_fast::run_ode_adaptive_shim,
-                             dfb_fast::run_dde_fixed_shim, {dfb_fast::launch_general_g1}, 1};
+                             dfb_fast::run_dde_fixed_shim, {dfb_fast::launch_general_g1}, 1,
+                             dfb_fast::run_dde_event_shim, dfb_fast::dde_event_query};
   out->strict = DfbLaunchTable{dfb_strict::run_ode_fixed_shim, dfb_strict::run_ode_fixed_periodic_shim,
                                dfb_strict::run_ode_event_shim, nullptr, nullptr,
-                               {dfb_strict::launch_general_g1}, 1};
+                               {dfb_strict::launch_general_g1}, 1, nullptr, nullptr};
   return 0;
 }

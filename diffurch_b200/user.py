@@ -33,6 +33,7 @@ def _jobs():
             jobs.append((src, f"{src[:-3]}_{tag}.o", [f"-DDFB_ARITH={arith}", "-DDFB_GROUP=1"] + extra))
     jobs.append(("kernels_ode_adaptive.cu", "kernels_ode_adaptive_fast.o", ["-DDFB_ARITH=1"]))
     jobs.append(("kernels_dde_fixed.cu", "kernels_dde_fixed_fast.o", ["-DDFB_ARITH=1"]))
+    jobs.append(("kernels_dde_event.cu", "kernels_dde_event_fast.o", ["-DDFB_ARITH=1"]))
     jobs.append(("plugin_entry.cu", "plugin_entry.o", []))
     return jobs
 

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define DFB_ABI_VERSION 2
+#define DFB_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define DFB_API __attribute__((visibility("default")))
@@ -320,6 +320,9 @@ typedef struct dfb_totals {
   double kernel_ms;        /* CUDA-event duration of the integration kernel(s) */
   uint32_t kernel_launches;
   uint32_t kernel_kind;    /* dfb_kernel_kind: which kernel family integrated the ensemble */
+  uint64_t locate_iters;   /* iterations of the location loops (Bisection / BisectionBool / RegulaFalsi,
+                              loc.rs:210-285) summed over the ensemble; counted by the event kernels
+                              (DFB_KERNEL_ODE_EVENT, DFB_KERNEL_DDE_EVENT), 0 elsewhere */
 } dfb_totals;
 
 /* Kernel families (all CUDA; there is no CPU path). */
@@ -330,8 +333,11 @@ typedef enum dfb_kernel_kind {
   DFB_KERNEL_ODE_ADAPTIVE = 3, /* ode_adaptive_kernel: AutomaticStepsize, dynamic trajectory queue */
   DFB_KERNEL_ODE_FIXED_PERIODIC = 4, /* ode_fixed_periodic_kernel: fixed step + Periodic callbacks
                                         (warp-uniform event handling; the Lyapunov-batch shape) */
-  DFB_KERNEL_ODE_EVENT = 5          /* ode_event_kernel: fixed step + located state-function events
+  DFB_KERNEL_ODE_EVENT = 5,         /* ode_event_kernel: fixed step + located state-function events
                                        (register-resident locators, warp-batched bisection) */
+  DFB_KERNEL_DDE_EVENT = 6          /* dde_event_kernel: fixed step DDE/NDDE + located events +
+                                       discontinuity propagation (per-lane coefficient ring with
+                                       stored start times, cached-record lookup) */
 } dfb_kernel_kind;
 
 /* Solver::new + setters -> one handle for `n_traj` trajectories on `device`. */

@@ -572,6 +572,92 @@ def test_dde_relay_clamp_strict_bit_exact(oracle):
     assert g.events[0] > 10
 
 
+# ---------------------------------------------------------------- dde_event_kernel (DDE + events + propagation)
+KERNEL_DDE_EVENT = 6
+
+
+def test_dde_event_kernel_relay_clamp_fast_vs_oracle(oracle):
+    # examples/dde-relay-clamp.rs:19-36 through the hot kernel: same event sequence, same step counts,
+    # event times within 1e-11, trajectory within 1e-10 of the (strict) oracle over t in [0, 20]
+    mk = lambda: cases.dde_relay_clamp(arith="fast", t1=20.0)
+    g = mk().run()
+    o = oracle.run_solver(cases.dde_relay_clamp(arith="strict", t1=20.0), n_threads=1)
+    assert g.totals["kernel_kind"] == KERNEL_DDE_EVENT and g.status[0] == 0
+    assert_same_counters(g, o)
+    n = int(g.event_n[0])
+    assert n == int(o.event_n[0]) and n > 10
+    assert np.array_equal(g.event_index[0, :n], o.event_index[0, :n])
+    assert np.allclose(g.event_t[0, :n], o.event_t[0, :n], rtol=0.0, atol=1e-11)
+    assert_same_trace(g, o, exact=False, rtol=1e-10, atol=1e-10)
+    assert g.totals["locate_iters"] > 40 * g.events[0]  # ~45 bisection iterations per located event
+
+
+def test_dde_event_kernel_equals_general_fast_kernel():
+    # the two FAST kernels implement the same arithmetic contract: same events, states within 1e-11
+    mk = lambda: cases.dde_relay_clamp_ensemble(96, arith="fast", t1=12.0, events=256, trace=d.Trace(7, 200))
+    hot = mk().run()
+    gen = run_general(mk)
+    assert hot.totals["kernel_kind"] == KERNEL_DDE_EVENT
+    assert np.array_equal(hot.steps, gen.steps) and np.array_equal(hot.events, gen.events)
+    assert np.array_equal(hot.status, gen.status) and np.all(hot.status == 0)
+    assert np.array_equal(hot.event_n, gen.event_n) and np.array_equal(hot.event_index, gen.event_index)
+    assert np.allclose(hot.event_t, gen.event_t, rtol=0.0, atol=1e-11)
+    assert np.allclose(hot.p, gen.p, rtol=1e-11, atol=1e-11)
+    assert_same_trace(hot, gen, exact=False, rtol=1e-11, atol=1e-11)
+
+
+def test_dde_event_kernel_ensemble_vs_oracle_ragged(oracle):
+    # 1000 members (a ragged last warp, members pulled from the work queue in any order): per-member
+    # results do not depend on the assignment; checked member by member against the oracle
+    mk = lambda a: cases.dde_relay_clamp_ensemble(1000, arith=a, t1=8.0, events=128)
+    g = mk("fast").run()
+    o = oracle.run_solver(mk("strict"), n_threads=8)
+    assert g.totals["kernel_kind"] == KERNEL_DDE_EVENT
+    assert_same_counters(g, o)
+    assert np.array_equal(g.event_n, o.event_n) and np.array_equal(g.event_index, o.event_index)
+    assert np.allclose(g.event_t, o.event_t, rtol=0.0, atol=1e-11)
+    assert np.allclose(g.p, o.p, rtol=1e-10, atol=1e-10)
+    g2 = mk("fast").run()
+    assert np.array_equal(g.p, g2.p) and np.array_equal(g.event_t, g2.event_t)  # run-to-run identical
+
+
+def test_dde_event_kernel_propagation_golden_vectors():
+    # tests/delay_propagation.rs:21-24, 45-50, 68-71, 91-93 in FAST arithmetic: the time grid of these
+    # problems is pure time arithmetic (rhs = 0), so the hot kernel must hit the exact f64 vectors too
+    g = cases.delay_constant_1().arith("fast").run()
+    assert g.totals["kernel_kind"] == KERNEL_DDE_EVENT
+    assert list(g.trace_t[0, :g.trace_n[0]]) == [0.0, 0.75, 1.0, 1.75, 2.0, 2.75, 3.0, 3.75, 4.0, 4.75, 5.0]
+    g = cases.delay_constant_2().arith("fast").run()
+    s = 7.0 / 8.0
+    assert g.totals["kernel_kind"] == KERNEL_DDE_EVENT
+    assert list(g.trace_t[0, :g.trace_n[0]]) == [0.0, s, 1.0, 1.25, 2., 2.25, 2.5, 3.0, 3.25, 3.5,
+                                                  3.75, 4., 4.25, 4.5, 4.75, 5.0]
+    g = cases.delay_constant_1_smoothing().arith("fast").run()
+    assert g.totals["kernel_kind"] == KERNEL_DDE_EVENT
+    assert list(g.trace_t[0, :g.trace_n[0]]) == [0., 0.75, 1., 1.75, 2., 2.75, 3., 3.75, 4.5, 5.25, 6.]
+    g = cases.delay_pantograph().arith("fast").run()
+    assert g.totals["kernel_kind"] == KERNEL_DDE_EVENT
+    ts = set(g.trace_t[0, :g.trace_n[0]])
+    for i in range(1, 11):
+        assert 2.0 ** i in ts
+
+
+def test_dde_event_kernel_panics_and_plain_dde(oracle):
+    # (a) a DDE without locators but with a trace + an on-step policy the streaming kernel does not take
+    #     (max_steps) lands here; (b) the reference's panics become the same status bits
+    mk = lambda a: cases.eq_dde_sin(k=np.linspace(0.6, 1.4, 40), t1=6.0, trace=True, arith=a).max_steps(100000)
+    g = mk("fast").run()
+    o = oracle.run_solver(mk("strict"), n_threads=4)
+    assert g.totals["kernel_kind"] == KERNEL_DDE_EVENT
+    assert_same_counters(g, o)
+    assert_same_trace(g, o, exact=False, rtol=1e-11, atol=1e-12)
+    s = lambda a: cases.eq_dde_sin(arith=a).max_delay(0.5).max_steps(100000)  # window shorter than the delay
+    g, o = s("fast").run(), oracle.run_solver(s("strict"))
+    assert g.totals["kernel_kind"] == KERNEL_DDE_EVENT
+    assert g.status[0] & d.abi.TRAJ_HISTORY_DELETED and o.status[0] & d.abi.TRAJ_HISTORY_DELETED
+    assert g.steps[0] == o.steps[0]
+
+
 # ---------------------------------------------------------------- adaptive
 def auto_stepsize(n_state, tol=1e-9):
     return d.AutomaticStepsize(stepsize=1e-2, stepsize_range=(1e-6, 1e-1), atol=[tol] * n_state,

@@ -10,7 +10,7 @@ import os
 from . import _abi as abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdiffurch_b200.so")
+LIB_PATH = os.environ.get("DFB_LIB_PATH") or os.path.join(_HERE, "libdiffurch_b200.so")  # DFB_LIB_PATH: A/B of two builds (tuning)
 
 
 class DfbError(RuntimeError):

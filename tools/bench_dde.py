@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import cases  # noqa: E402
 import diffurch_b200 as d  # noqa: E402
 
-n = 1 << 18
+n = int(sys.argv[sys.argv.index("--members") + 1]) if "--members" in sys.argv else 1 << 18
 k = 0.5 + np.arange(n) / (n - 1.0)
 prm = cases.dde_params(k)
 ens = (d.Solver.new().max_delay(1.0).initial(d.InitFn(d.SIN)).interval(0.0, 100.0).stepsize(0.02)

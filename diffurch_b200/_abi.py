@@ -163,6 +163,7 @@ class Totals(C.Structure):
 EXPORTED_SYMBOLS = [
     "dfb_tableau_by_name", "dfb_tableau_generic_order_2", "dfb_tableau_generic_order_3",
     "dfb_problem_default", "dfb_system_info_get", "dfb_register_plugin",
+    "dfb_register_system_from_source", "dfb_nvrtc_stats", "dfb_nvrtc_prebuild",
     "dfb_create", "dfb_destroy",
     "dfb_set_initial", "dfb_set_params", "dfb_set_initial_device", "dfb_set_params_device",
     "dfb_run", "dfb_synchronize",

@@ -35,6 +35,9 @@ def _load():
         "dfb_problem_default": (C.c_int, [C.POINTER(abi.Problem)]),
         "dfb_system_info_get": (C.c_int, [C.c_int32, C.POINTER(abi.SystemInfo)]),
         "dfb_register_plugin": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32)]),
+        "dfb_register_system_from_source": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_int32)]),
+        "dfb_nvrtc_stats": (C.c_int, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), dp, dp]),
+        "dfb_nvrtc_prebuild": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(abi.Tableau), C.c_int32, C.c_int32]),
         "dfb_create": (C.c_int, [C.POINTER(abi.Problem), C.c_size_t, C.c_int, C.POINTER(H)]),
         "dfb_destroy": (None, [H]),
         "dfb_set_initial": (C.c_int, [H, dp]),

@@ -32,6 +32,7 @@ def _jobs():
     jobs.append(("kernels_dde_fixed.cu", "dde_fixed_fast.o", ["-DDFB_ARITH=1"]))
     jobs.append(("kernels_dde_event.cu", "dde_event_fast.o", ["-DDFB_ARITH=1"]))
     jobs.append(("kernels_ode_adaptive.cu", "ode_adaptive_fast.o", ["-DDFB_ARITH=1"]))
+    jobs.append(("nvrtc_systems.cu", "nvrtc_systems.o", []))
     jobs.append(("api.cu", "api.o", []))
     return jobs
 

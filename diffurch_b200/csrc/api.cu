@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <string>
 #include <vector>
@@ -22,6 +23,7 @@
 #include "launch.hpp"
 
 #include "launch_table.hpp"
+#include "nvrtc_systems.hpp"
 
 // Launchers exported by the kernel translation units (argument blocks are declared per
 // arithmetic namespace in dev/*.cuh; the shims take plain arguments).
@@ -330,7 +332,8 @@ int launch_general(dfb_handle* h, const DevProblem& P, cudaStream_t stream) {
     const int rc = T.general[g](P, h->prob.system_id, has_loc, cfg, h->locate_batch);
     if (rc == -1) continue;
     if (rc != 0)
-      return fail(DFB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(cudaError_t(rc)));
+      return fail(DFB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(cudaError_t(rc)) +
+                                    (dfb_nvrtc_last_error()[0] ? std::string(" / ") + dfb_nvrtc_last_error() : std::string()));
     return DFB_OK;
   }
   return fail(DFB_ERR_UNSUPPORTED,
@@ -451,6 +454,50 @@ int dfb_register_plugin(const char* so_path, int32_t* system_id_out) {
   ps->strict = d.strict;
   plugins().push_back(ps);
   *system_id_out = id;
+  return DFB_OK;
+}
+
+// Solver::equation from SOURCE text (csrc/nvrtc_systems.cu): compiled with NVRTC, kernel by kernel, on
+// first use.  Registering the same (source, struct) twice returns the same id.
+int dfb_register_system_from_source(const char* cuda_source, const char* struct_name, int32_t* system_id_out) {
+  if (!cuda_source || !struct_name || !system_id_out) return fail(DFB_ERR_INVALID, "null argument");
+  const std::string path = std::string("nvrtc:") + struct_name + ":" + std::to_string(std::hash<std::string>{}(cuda_source));
+  for (size_t i = 0; i < plugins().size(); ++i)
+    if (plugins()[i]->path == path) {
+      *system_id_out = DFB_SYS_USER_BASE + int32_t(i);
+      return DFB_OK;
+    }
+  const int id = DFB_SYS_USER_BASE + int(plugins().size());
+  dfb_nvrtc_sysinfo d;
+  PluginSys* ps = new PluginSys();
+  if (dfb_nvrtc_register(cuda_source, struct_name, id, &d, &ps->fast, &ps->strict) != 0) {
+    delete ps;
+    return fail(DFB_ERR_INVALID, std::string("dfb_register_system_from_source: ") + dfb_nvrtc_last_error());
+  }
+  if (d.n_state < 1 || d.n_state > DFB_MAX_STATE || d.n_params < 0 || d.n_params > DFB_MAX_PARAMS || d.n_aux < 0 ||
+      d.n_aux > DFB_MAX_AUX) {
+    delete ps;
+    return fail(DFB_ERR_INVALID, "source system exceeds DFB_MAX_STATE / DFB_MAX_PARAMS / DFB_MAX_AUX");
+  }
+  ps->info = SysInfo{id, d.n_state, d.n_params, d.n_aux, d.n_detectors, d.n_callbacks, d.uses_history};
+  ps->dde_hot_ok = false;
+  ps->name = struct_name;
+  ps->path = path;
+  ps->dl = nullptr;
+  plugins().push_back(ps);
+  *system_id_out = id;
+  return DFB_OK;
+}
+
+int dfb_nvrtc_stats(uint32_t* kernels_compiled, uint32_t* disk_cache_hits, double* compile_ms_total, double* last_compile_ms) {
+  dfb_nvrtc_get_stats(kernels_compiled, disk_cache_hits, compile_ms_total, last_compile_ms);
+  return DFB_OK;
+}
+
+int dfb_nvrtc_prebuild(int32_t system_id, int32_t arith, const dfb_tableau* rk, int32_t members_per_thread, int32_t trace) {
+  if (!rk) return fail(DFB_ERR_INVALID, "null argument");
+  if (dfb_nvrtc_prebuild_ode_fixed(system_id, arith, rk, members_per_thread, trace) != 0)
+    return fail(DFB_ERR_INVALID, std::string("dfb_nvrtc_prebuild: ") + dfb_nvrtc_last_error());
   return DFB_OK;
 }
 
@@ -691,7 +738,9 @@ int dfb_run(dfb_handle* h, void* stream_v) {
     const int rc = !shim ? -1 : shim(p.system_id, p.rk, p.t0, p.t1, p.h, n, y0, params, h->d_t, h->d_y,
                         h->d_steps, h->d_rhs, h->d_status, tracing ? p.trace_every : 0, p.trace_capacity,
                         tracing ? h->d_trace_t : nullptr, h->d_trace_y, h->d_nsamples, stream);
-    if (rc > 0) return fail(DFB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(cudaError_t(rc)));
+    if (rc > 0)
+      return fail(DFB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(cudaError_t(rc)) +
+                                    (dfb_nvrtc_last_error()[0] ? std::string(" / ") + dfb_nvrtc_last_error() : std::string()));
     if (rc == 0) {
       DFB_CUDA(cudaEventRecord(h->ev1, stream));
       h->launches = 1;

@@ -34,6 +34,36 @@ __device__ __forceinline__ double dev_powi(double a, int b) {
   return recip ? 1.0 / r : r;
 }
 
+// n-th root in plain IEEE +, *, / (frexp / ldexp are exact): STRICT builds use it where the reference
+// calls f64::powf (stepsize.rs:74) so that the adaptive path is bit-identical to the CPU oracle run with
+// the same function (oracle/diffurch_oracle.hpp `portable_root`; libm pow differs between platforms in
+// its last bit and CUDA's pow is not glibc's).  Within 2 ulp of pow(x, 1/n) for 1e-4 < x < 1e4.
+__device__ inline double dev_portable_root(double x, unsigned n) {
+  if (x != x) return x;
+  if (x < 0.0) return __longlong_as_double(0x7ff8000000000000LL);
+  if (x == 0.0) return 0.0;
+  if (x == __longlong_as_double(0x7ff0000000000000LL)) return x;
+  if (n <= 1u) return x;
+  int e = 0;
+  const double m = frexp(x, &e);
+  int q = e / int(n), r = e - q * int(n);
+  if (r < 0) {
+    r += int(n);
+    q -= 1;
+  }
+  const double a = ldexp(m, r);
+  double y = a > 1.0 ? a : 1.0;
+  const double nm1 = double(n - 1u), dn = double(n);
+#pragma unroll 1
+  for (int it = 0; it < 48; ++it) {
+    double p = 1.0;
+#pragma unroll 1
+    for (unsigned j = 0; j + 1u < n; ++j) p = p * y;
+    y = (nm1 * y + a / p) / dn;
+  }
+  return ldexp(y, q);
+}
+
 // Tableau accessor over the kernel parameter block, compile-time shape.
 // RT = run-time shape: the kernel is instantiated for the maximal shape (S_, I_ = array sizes and
 // unroll bounds) and every stage / interpolant loop iteration is additionally guarded by the
@@ -490,7 +520,11 @@ struct Integrator {
       const double e = ae / (A.atol[n] + ae * A.rtol[n]);
       err = n == 0 ? e : fmax(err, e);
     }
+#if DFB_ARITH == 0
+    double factor = A.fac * dev_portable_root(1.0 / err, A.order + 1u);
+#else
     double factor = A.fac * pow(1.0 / err, 1.0 / double(A.order + 1u));
+#endif
     factor = dev_clamp(factor, A.fac_min, A.fac_max);
     h_auto *= factor;
     h_auto = dev_clamp(h_auto, A.stepsize_min, A.stepsize_max);

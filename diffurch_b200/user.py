@@ -107,3 +107,33 @@ def load_user_system(so_path, name=None, params=(), detectors=None, callbacks=No
                                    n_aux=info.n_aux, detectors=dict(detectors or {}),
                                    callbacks=dict(callbacks or {}), uses_history=bool(info.uses_history),
                                    reference=reference))
+
+
+def load_user_system_from_source(source, struct_name, name=None, params=(), detectors=None, callbacks=None,
+                                 reference=""):
+    """Register a device functor given as SOURCE TEXT; no nvcc needed.  The functor is compiled at run time
+    with NVRTC (`dfb_register_system_from_source`), one kernel instantiation at a time on first use, from
+    the same kernel templates as the built-in systems.  Fixed-step problems without events take the
+    register-resident hot kernel, everything else the general kernel."""
+    if os.path.exists(source):
+        source = open(source).read()
+    sid = C.c_int32()
+    check(lib.dfb_register_system_from_source(source.encode(), struct_name.encode(), C.byref(sid)))
+    info = abi.SystemInfo()
+    check(lib.dfb_system_info_get(sid.value, C.byref(info)))
+    params = tuple(params)
+    if len(params) != info.n_params:
+        raise ValueError(f"the functor declares NP = {info.n_params} parameters, {len(params)} names given")
+    from . import systems
+    return systems.register(System(name or struct_name, sid.value, info.n_state, params, n_aux=info.n_aux,
+                                   detectors=dict(detectors or {}), callbacks=dict(callbacks or {}),
+                                   uses_history=bool(info.uses_history), reference=reference))
+
+
+def nvrtc_stats():
+    """Run-time compilation counters: kernels compiled, disk-cache hits, total / last compile time (ms)."""
+    a, b = C.c_uint32(), C.c_uint32()
+    t, l = C.c_double(), C.c_double()
+    check(lib.dfb_nvrtc_stats(C.byref(a), C.byref(b), C.byref(t), C.byref(l)))
+    return {"kernels_compiled": a.value, "disk_cache_hits": b.value, "compile_ms_total": t.value,
+            "last_compile_ms": l.value}

@@ -300,6 +300,25 @@ DFB_API int dfb_system_info_get(int32_t system_id, dfb_system_info* out);
  * the same path twice returns the same id.  Plugins stay loaded for the life of the process. */
 DFB_API int dfb_register_plugin(const char* so_path, int32_t* system_id_out);
 
+/* The same from SOURCE text: the functor is compiled at run time with NVRTC for sm_100a (no nvcc on the
+ * machine), one kernel instantiation at a time, on first use — the exact tableau sparsity, arithmetic
+ * contract and trace policy a problem asks for; CUBINs are cached in memory and on disk (DFB_NVRTC_CACHE).
+ * `cuda_source` is what a user-system header holds; it may omit the
+ * `#include "user_system.cuh"` / `namespace DFB_NS {}` wrapper.  Fixed-step ODE problems without events run in
+ * ode_fixed_kernel, everything else in integrate_general_kernel — the same templates as the built-in
+ * systems, so results are bit-identical to the nvcc-built plugin of the same functor.  Registration needs no
+ * GPU (the functor's static facts are read from NVRTC's output); running does. */
+DFB_API int dfb_register_system_from_source(const char* cuda_source, const char* struct_name,
+                                            int32_t* system_id_out);
+/* Run-time compilation counters of this process: kernels compiled, disk-cache hits, total and last compile
+ * time in milliseconds.  NULL pointers are skipped. */
+DFB_API int dfb_nvrtc_stats(uint32_t* kernels_compiled, uint32_t* disk_cache_hits, double* compile_ms_total,
+                            double* last_compile_ms);
+/* Compile (or fetch from the cache) the ode_fixed_kernel instantiation of a source-registered system for
+ * `rk` without launching it: pays the compile time up front; works without a GPU. */
+DFB_API int dfb_nvrtc_prebuild(int32_t system_id, int32_t arith, const dfb_tableau* rk,
+                               int32_t members_per_thread, int32_t trace);
+
 /* ------------------------------------------------------------------ handle */
 typedef struct dfb_handle dfb_handle;
 

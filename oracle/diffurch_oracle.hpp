@@ -428,6 +428,40 @@ struct State {
 // ---------------------------------------------------------------------------
 enum class StepStatus { Rejected, Accepted };
 
+// The reference computes the step-size factor with f64::powf, i.e. the platform's libm `pow`
+// (stepsize.rs:74): its last bit differs between libm builds, and CUDA's pow is not glibc's.  To pin the
+// CONTROL FLOW of the adaptive path (error norm, clamps, reject loop, k[0] re-evaluation) bit for bit on
+// the GPU, the n-th root can be switched to `portable_root`: frexp / ldexp (exact) and a fixed number of
+// Newton steps in plain IEEE +, *, / — the same bits on any IEEE machine compiled without contraction.
+// The STRICT CUDA build always uses its own copy of this function (csrc/dev/integrator.cuh); the oracle
+// uses it when `g_portable_root` is set (tests), libm pow otherwise (the reference's behaviour).  It agrees
+// with pow(x, 1/n) to 2 ulp for 1e-4 < x < 1e4 (up to 10 ulp at |ln x| = 60: pow's exponent is the ROUNDED
+// 1/n, so pow itself is that far from the n-th root; tests/test_oracle_independent.py).
+inline bool g_portable_root = false;
+inline double portable_root(double x, unsigned n) {
+  if (x != x) return x;
+  if (x < 0.0) return std::numeric_limits<double>::quiet_NaN();
+  if (x == 0.0) return 0.0;                                            // pow(0, 1/n) = 0
+  if (x == std::numeric_limits<double>::infinity()) return x;          // pow(inf, 1/n) = inf
+  if (n <= 1u) return x;
+  int e = 0;
+  const double m = std::frexp(x, &e);                                  // x = m 2^e, m in [0.5, 1)
+  int q = e / int(n), r = e - q * int(n);
+  if (r < 0) {
+    r += int(n);
+    q -= 1;
+  }
+  const double a = std::ldexp(m, r);                                   // a in [0.5, 2^(n-1)), x = a 2^(q n)
+  double y = a > 1.0 ? a : 1.0;                                        // Newton from above: monotone, then quadratic
+  const double nm1 = double(n - 1u), dn = double(n);
+  for (int it = 0; it < 48; ++it) {
+    double p = 1.0;
+    for (unsigned j = 0; j + 1u < n; ++j) p = p * y;                   // y^(n-1)
+    y = (nm1 * y + a / p) / dn;
+  }
+  return std::ldexp(y, q);
+}
+
 template <int N>
 struct Stepsize {
   bool automatic = false;
@@ -450,7 +484,7 @@ struct Stepsize {
       err = first ? e : std::fmax(err, e);
       first = false;
     }
-    double factor = fac * std::pow(1.0 / err, 1.0 / double(order + 1));
+    double factor = fac * (g_portable_root ? portable_root(1.0 / err, order + 1u) : std::pow(1.0 / err, 1.0 / double(order + 1)));
     factor = clamp(factor, fac_lo, fac_hi);
     stepsize *= factor;
     stepsize = clamp(stepsize, range_lo, range_hi);

@@ -59,6 +59,10 @@ def lib():
         L.orc_householder_qr3.argtypes = [dp, dp, dp]
         L.orc_powi.restype = C.c_double
         L.orc_powi.argtypes = [C.c_double, C.c_int]
+        L.orc_set_portable_root.restype = None
+        L.orc_set_portable_root.argtypes = [C.c_int]
+        L.orc_portable_root.restype = C.c_double
+        L.orc_portable_root.argtypes = [C.c_double, C.c_uint]
         L.orc_system_info.restype = C.c_int
         L.orc_system_info.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                       C.POINTER(C.c_int)]
@@ -134,7 +138,13 @@ def run(problem, y0, params=None, n_threads=1):
     return r
 
 
-def run_solver(solver, n_threads=1):
-    """Run the oracle on what a diffurch_b200.Solver builder describes."""
+def run_solver(solver, n_threads=1, portable_root=False):
+    """Run the oracle on what a diffurch_b200.Solver builder describes.  `portable_root`: compute the
+    AutomaticStepsize factor with the portable n-th root the STRICT CUDA build uses instead of libm pow
+    (see diffurch_oracle.hpp)."""
     n, y0, params = solver._resolve()
-    return run(solver.problem(), y0, params, n_threads=n_threads)
+    lib().orc_set_portable_root(1 if portable_root else 0)
+    try:
+        return run(solver.problem(), y0, params, n_threads=n_threads)
+    finally:
+        lib().orc_set_portable_root(0)

@@ -462,4 +462,8 @@ void orc_householder_qr3(const double* a, double* q, double* rdiag) {
 
 double orc_powi(double a, int b) { return powi(a, b); }
 
+// the n-th root used instead of libm pow by the STRICT CUDA build; `on` != 0 makes orc_run use it too
+void orc_set_portable_root(int on) { g_portable_root = on != 0; }
+double orc_portable_root(double x, unsigned n) { return portable_root(x, n); }
+
 }  // extern "C"

@@ -572,6 +572,31 @@ def test_dde_relay_clamp_strict_bit_exact(oracle):
     assert g.events[0] > 10
 
 
+def test_adaptive_strict_is_step_for_step_identical_to_the_golden_and_the_oracle(oracle):
+    # STRICT adaptive (general kernel): error norm, clamps, reject loop, k[0] re-evaluation and the portable
+    # n-th root are the oracle's operations in the oracle's order -> every accepted step, every rejection and
+    # the final state are bit-identical to tests/golden/adaptive_golden.json ("portable_root" variant, frozen
+    # from an independent numpy restatement) and to the oracle run with the same root
+    import json
+    import test_oracle_independent as ti
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "adaptive_golden.json")))["cases"]
+    for name, sys_name, rk_name, y0, prm, t0, t1, ctl in ti.adaptive_cases():
+        mk = lambda: ti.adaptive_solver(sys_name, rk_name, y0, prm, t0, t1, ctl, arith="strict").on_step(d.Trace(1, 12000))
+        g = mk().run()
+        e = gold[name]["portable_root"]
+        assert g.totals["kernel_kind"] == KERNEL_GENERAL and g.status[0] == 0, name
+        assert [int(g.steps[0]), int(g.rejected[0]), int(g.rhs_evals[0])] == e["steps_rejected_evals"], name
+        assert float(g.t[0]).hex() == e["t"] and [float(v).hex() for v in g.p[0]] == e["p"], name
+        o = oracle.run_solver(mk(), n_threads=1, portable_root=True)
+        assert_same_counters(g, o)
+        assert_same_trace(g, o, exact=True)   # every accepted step: same time, same state, bit for bit
+        # FAST hot kernel (MUFU-seeded root, FMA): same problem within the solver tolerance
+        f = ti.adaptive_solver(sys_name, rk_name, y0, prm, t0, t1, ctl, arith="fast").run()
+        assert f.status[0] == 0 and abs(int(f.steps[0]) - int(g.steps[0])) <= max(2, int(g.steps[0]) // 50), name
+        scale = np.maximum(np.abs(g.p[0]), 1.0)
+        assert np.all(np.abs(f.p[0] - g.p[0]) / scale < 2e3 * max(ctl["atol"][0], 1e-9)), (name, f.p[0], g.p[0])
+
+
 # ---------------------------------------------------------------- dde_event_kernel (DDE + events + propagation)
 KERNEL_DDE_EVENT = 6
 

@@ -143,6 +143,9 @@ extern "C" {
     pub fn dfb_tableau_generic_order_3(c2: f64, c3: f64, has_b3: c_int, b3: f64, out: *mut dfb_tableau) -> c_int;
     pub fn dfb_problem_default(p: *mut dfb_problem) -> c_int;
     pub fn dfb_system_info_get(system_id: i32, out: *mut dfb_system_info) -> c_int;
+    pub fn dfb_register_system_from_source(cuda_source: *const c_char, struct_name: *const c_char, system_id_out: *mut i32) -> c_int;
+    pub fn dfb_nvrtc_stats(kernels_compiled: *mut u32, disk_cache_hits: *mut u32, compile_ms_total: *mut f64, last_compile_ms: *mut f64) -> c_int;
+    pub fn dfb_nvrtc_prebuild(system_id: i32, arith: i32, rk: *const dfb_tableau, members_per_thread: i32, trace: i32) -> c_int;
     pub fn dfb_register_plugin(so_path: *const c_char, system_id_out: *mut i32) -> c_int;
     pub fn dfb_create(desc: *const dfb_problem, n_traj: usize, device: c_int, out: *mut *mut dfb_handle) -> c_int;
     pub fn dfb_destroy(h: *mut dfb_handle);

@@ -268,6 +268,10 @@ int validate(const dfb_problem& p, const SysInfo** info_out) {
     return fail(DFB_ERR_INVALID, "history_id");
   if ((p.history_id == DFB_HIST_SIN || p.history_id == DFB_HIST_SIN_NODERIV) && info->n_params < 4)
     return fail(DFB_ERR_INVALID, "sin history needs a system with parameter k (index 3)");
+  // the registered InitFn closures are scalar (initial_condition.rs tests use N = 1): a wider system would
+  // silently get zeros in components 1..N-1
+  if (p.history_id != DFB_HIST_CONSTANT && info->n_state != 1)
+    return fail(DFB_ERR_INVALID, "the registered history functions (InitFn) are defined for N = 1 systems only");
   if (std::isnan(p.t0) || std::isnan(p.t1)) return fail(DFB_ERR_INVALID, "interval");
   for (int l = 0; l < p.n_loc; ++l) {
     const dfb_locator& L = p.loc[l];

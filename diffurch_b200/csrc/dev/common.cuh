@@ -5,9 +5,13 @@
 //                                 the reference's operation order: bit-parity mode)
 //   -DDFB_ARITH=1              -> namespace dfb_fast   (FMA contraction allowed)
 #pragma once
+#ifdef __CUDACC_RTC__
+typedef struct CUstream_st* cudaStream_t;  // NVRTC: device code only; LaunchCfg below just needs the name
+#else
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #include "../../../include/diffurch_b200.h"
 

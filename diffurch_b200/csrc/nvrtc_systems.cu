@@ -415,21 +415,28 @@ bool probe(SourceSys* S) {
     g_error = "could not read the functor's static facts from the NVRTC probe";
     return false;
   }
-  int v[10] = {0};
+  // NVRTC prints the array either as 10 .b32 words or as 40 .b8 bytes (little endian, trailing zeros cut)
+  const bool bytes = text.rfind(".b8", at) != std::string::npos && text.rfind(".b8", at) > text.rfind('\n', at);
+  long raw[40] = {0};
   int k = 0;
   const char* p = text.c_str() + lb + 1;
   const char* end = text.c_str() + rb;
-  while (p < end && k < 10) {
+  while (p < end && k < 40) {
     char* q = nullptr;
     const long x = std::strtol(p, &q, 10);
     if (q == p) {
       ++p;
       continue;
     }
-    v[k++] = int(x);
+    raw[k++] = x;
     p = q;
   }
-  if (k != 10 || v[9] != 12345) {
+  int v[10] = {0};
+  for (int i = 0; i < 10; ++i)
+    v[i] = bytes ? int(unsigned(raw[4 * i]) | (unsigned(raw[4 * i + 1]) << 8) | (unsigned(raw[4 * i + 2]) << 16) |
+                       (unsigned(raw[4 * i + 3]) << 24))
+                 : int(raw[i]);
+  if (v[9] != 12345) {
     g_error = "unexpected NVRTC probe output";
     return false;
   }

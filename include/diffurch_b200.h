@@ -26,8 +26,17 @@
 #ifndef DIFFURCH_B200_H
 #define DIFFURCH_B200_H
 
+#ifdef __CUDACC_RTC__
+/* run-time compilation (NVRTC) has no system headers: the LP64 types this header uses */
+typedef unsigned long size_t;
+typedef unsigned long uint64_t;
+typedef long int64_t;
+typedef unsigned int uint32_t;
+typedef int int32_t;
+#else
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {

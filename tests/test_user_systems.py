@@ -212,3 +212,127 @@ def test_callback_may_switch_a_captured_parameter(built):
     assert np.array_equal(gen.p, s.p) and np.array_equal(gen.event_t, s.event_t) and np.array_equal(gen.aux, s.aux)
     f = mk("fast").run()
     assert np.array_equal(f.aux, s.aux) and np.max(np.abs(f.event_t - s.event_t)) < 1e-10
+
+
+# ---------------------------------------------------------------------------- from SOURCE (NVRTC)
+VDP_SOURCE = open(plugins.header("van_der_pol")).read()
+INLINE_SOURCE = """
+struct SysDuffingInline : SysBase {          // x'' + delta x' + alpha x + beta x^3 = 0, no wrapper around it
+  static constexpr int N = 2, NP = 3;
+  template <class V>
+  __device__ __forceinline__ static void rhs(const V& s, const double* prm, double* out) {
+    out[0] = s.p[1];
+    out[1] = -prm[0] * s.p[1] - prm[1] * s.p[0] - prm[2] * (s.p[0] * s.p[0]) * s.p[0];
+  }
+};
+"""
+
+
+def test_source_system_registers_and_builds_without_a_gpu_or_nvcc(tmp_path, monkeypatch):
+    """dfb_register_system_from_source: the functor's static facts come out of NVRTC's output (no GPU, no
+    nvcc on PATH), and the kernel instantiation a problem needs compiles to a CUBIN for sm_100a."""
+    monkeypatch.setenv("PATH", "/nonexistent")            # nvcc is not reachable
+    monkeypatch.setenv("DFB_NVRTC_CACHE", str(tmp_path))
+    vdp = user.load_user_system_from_source(VDP_SOURCE, "SysVanDerPol", params=("mu",), detectors={"x": 1},
+                                            callbacks={"count": 1})
+    assert vdp.id >= d.abi.SYS_USER_BASE and (vdp.n_state, vdp.n_params, vdp.n_aux) == (2, 1, 1)
+    again = user.load_user_system_from_source(VDP_SOURCE, "SysVanDerPol", params=("mu",))
+    assert again.id == vdp.id                              # idempotent per (source, struct)
+    duf = user.load_user_system_from_source(INLINE_SOURCE, "SysDuffingInline", params=("delta", "alpha", "beta"))
+    assert duf.id != vdp.id and duf.n_state == 2 and not duf.uses_history
+    before = user.nvrtc_stats()
+    for arith in (d.abi.ARITH_FAST, d.abi.ARITH_STRICT):
+        rk = d.RK.rktp64()
+        assert d.lib.dfb_nvrtc_prebuild(vdp.id, arith, C.byref(rk), 2, 0) == 0, d.lib.dfb_last_error()
+    rk4 = d.RK.rk4()
+    assert d.lib.dfb_nvrtc_prebuild(duf.id, d.abi.ARITH_FAST, C.byref(rk4), 1, 1) == 0, d.lib.dfb_last_error()
+    after = user.nvrtc_stats()
+    assert after["kernels_compiled"] == before["kernels_compiled"] + 3 and after["last_compile_ms"] > 0.0
+    assert len([f for f in os.listdir(tmp_path) if f.endswith(".cubin")]) == 3
+    # the same request again is served from the disk cache
+    assert d.lib.dfb_nvrtc_prebuild(duf.id, d.abi.ARITH_FAST, C.byref(rk4), 1, 1) == 0
+    assert user.nvrtc_stats()["disk_cache_hits"] == after["disk_cache_hits"] + 1
+    sid = C.c_int32()
+    assert d.lib.dfb_register_system_from_source(b"struct Broken : SysBase { int", b"Broken", C.byref(sid)) == d.abi.ERR_INVALID
+    assert b"NVRTC" in d.lib.dfb_last_error()
+    assert d.lib.dfb_nvrtc_prebuild(d.abi.SYS_LORENZ, 1, C.byref(rk4), 1, 0) == d.abi.ERR_INVALID  # not a source system
+
+
+@pytest.mark.gpu
+def test_source_systems_are_bit_identical_to_the_nvcc_plugins(built, tmp_path, monkeypatch):
+    """Van der Pol and the user Lorenz restatement, registered from source with nvcc absent from PATH: the
+    hot fixed-step kernel (exact tableau sparsity) and the general kernel give the same bits as the plugin
+    built by nvcc from the same functor; the first-call compile time is reported."""
+    monkeypatch.setenv("PATH", "/nonexistent")
+    monkeypatch.setenv("DFB_NVRTC_CACHE", str(tmp_path))
+    vdp_p = user.load_user_system(built["van_der_pol"], name="van_der_pol", params=("mu",), detectors={"x": 1},
+                                  callbacks={"count": 1})
+    vdp_s = user.load_user_system_from_source(VDP_SOURCE, "SysVanDerPol", name="van_der_pol_src", params=("mu",),
+                                              detectors={"x": 1}, callbacks={"count": 1})
+    lor_p = user.load_user_system(built["user_lorenz"], params=("sigma", "rho", "beta"))
+    lor_s = user.load_user_system_from_source(plugins.header("user_lorenz"), "SysUserLorenz", name="user_lorenz_src",
+                                              params=("sigma", "rho", "beta"))
+    mu = np.linspace(0.3, 3.5, 333).reshape(-1, 1)
+    n = 300
+    prm = np.stack([np.full(n, 10.0), 20.0 + 20.0 * np.arange(n) / (n - 1), np.full(n, 8.0 / 3.0)], axis=1)
+    auto = d.AutomaticStepsize(1e-2, (1e-6, 1e-1), [1e-9] * 3, [1e-9] * 3, 4, 0.9, (0.2, 5.0))
+    t_first = None
+    for arith in ("strict", "fast"):
+        for variant in ("fixed", "rk4", "trace", "adaptive", "event"):
+            def mk_vdp(system):
+                s = (d.Solver.new().initial(np.tile([2.0, 0.0], (333, 1))).equation(system, mu).interval(0.0, 3.0)
+                     .stepsize(0.01).arith(arith))
+                if variant == "rk4":
+                    s = s.rk(d.RK.rk4())
+                if variant == "trace":
+                    s = s.on_step(d.Trace(25, 16))
+                if variant == "adaptive":
+                    s = s.stepsize(d.AutomaticStepsize(1e-2, (1e-6, 1e-1), [1e-9] * 2, [1e-9] * 2, 4, 0.9, (0.2, 5.0)))
+                if variant == "event":
+                    s = s.on_mut(d.Locator.zero("x"), "count").log_events(d.EventLog(16))
+                return s
+
+            def mk_lor(system):
+                s = d.Solver.new().initial(np.tile([1.0, 2.0, 20.0], (n, 1))).equation(system, prm).interval(0.0, 2.0).stepsize(1.0 / 250.0).arith(arith)
+                if variant == "rk4":
+                    s = s.rk(d.RK.rk4())
+                if variant == "trace":
+                    s = s.on_step(d.Trace(50, 16))
+                if variant == "adaptive":
+                    s = s.stepsize(auto)
+                return s
+            before = user.nvrtc_stats()
+            a, b = mk_vdp(vdp_s).run(), mk_vdp(vdp_p).run()
+            if t_first is None:
+                t_first = user.nvrtc_stats()["last_compile_ms"]
+            hot = variant in ("fixed", "rk4", "trace")
+            assert a.totals["kernel_kind"] == (d.abi.KERNEL_ODE_FIXED if hot else d.abi.KERNEL_GENERAL), (arith, variant)
+            # the plugin takes the adaptive / event HOT kernels where the source system takes the general one:
+            # the same bits in STRICT (one arithmetic contract), the FAST tolerance otherwise
+            exact = hot or arith == "strict"
+            if exact:
+                assert np.array_equal(a.p, b.p) and np.array_equal(a.t, b.t) and np.array_equal(a.steps, b.steps), (arith, variant)
+                assert np.array_equal(a.rhs_evals, b.rhs_evals), (arith, variant)
+            else:
+                assert np.max(np.abs(a.p - b.p)) < 1e-7 and np.max(np.abs(a.steps.astype(np.int64) - b.steps.astype(np.int64))) <= 2
+            assert np.all(a.status == 0), (arith, variant)
+            if variant == "trace":
+                assert np.array_equal(a.trace_p, b.trace_p) and np.array_equal(a.trace_n, b.trace_n)
+            if variant == "event":
+                assert np.array_equal(a.events, b.events) and np.array_equal(a.aux, b.aux) and np.sum(a.events) >= 100
+                assert np.array_equal(a.event_t, b.event_t) if exact else np.max(np.abs(a.event_t - b.event_t)) < 1e-10
+            if variant == "adaptive" and exact:
+                assert np.array_equal(a.rejected, b.rejected)
+            if variant != "event":
+                u, v = mk_lor(lor_s).run(), mk_lor(lor_p).run()
+                if exact:
+                    assert np.array_equal(u.p, v.p) and np.array_equal(u.steps, v.steps), (arith, variant)
+                    assert np.array_equal(u.p, mk_lor(d.systems.Lorenz).run().p), (arith, variant)
+                else:
+                    assert np.max(np.abs(u.p - v.p) / np.maximum(np.abs(v.p), 1.0)) < 1e-5, (arith, variant)
+                assert np.all(u.status == 0)
+            assert user.nvrtc_stats()["kernels_compiled"] >= before["kernels_compiled"]
+    st = user.nvrtc_stats()
+    assert st["kernels_compiled"] >= 10 and t_first is not None and t_first > 0.0
+    print(f"[nvrtc] {st['kernels_compiled']} kernels compiled in {st['compile_ms_total']:.0f} ms "
+          f"(first call {t_first:.0f} ms, mean {st['compile_ms_total'] / st['kernels_compiled']:.0f} ms)")

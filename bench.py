@@ -200,7 +200,7 @@ def run_reference(args, rank, world):
               f"{cores} std::thread workers, one Solver per member; oracle built -O2 -ffp-contract=off")
     cpu = {"value": value, "unit": "RK steps/s", "cores": cores, "kind": "port", "sample": sample}
     if not os.environ.get("DFB_BENCH_SKIP_DDE"):
-        n_dde = max(cores, int(os.environ.get("DFB_BENCH_REF_SAMPLE", 128 * cores)) // 4)
+        n_dde = max(cores, int(os.environ.get("DFB_BENCH_REF_SAMPLE", 4096 * cores)) // 4)
         dr, ddt, _ = cpu_oracle_rate_dde(n_dde, cores)
         cpu["dde"] = {"value": dr, "unit": "RK steps/s", "cores": cores, "kind": "port",
                       "sample": f"{n_dde} members of the k sweep x {DDE_STEPS_PER_MEMBER} steps ({ddt:.1f} s)"}
@@ -530,11 +530,17 @@ def main():
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
+    # stdout carries exactly ONE line (the JSON): whatever libraries print there (NCCL's version banner
+    # under NCCL_DEBUG=VERSION, for one) goes to stderr instead
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: diffurch_b200 has no CPU path"}))
+        json_out.write(json.dumps({"error": "no CUDA device: diffurch_b200 has no CPU path"}) + "\n")
+        json_out.flush()
         return 1
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -660,7 +666,8 @@ def main():
         "other_scaling": other_scaling,
         "other_configs": others,
     }
-    print(json.dumps(line))
+    json_out.write(json.dumps(line) + "\n")
+    json_out.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -40,7 +40,9 @@ namespace DFB_NS {
 // is the shape of the shipped event examples; knowing it at compile time removes the Periodic,
 // filter, boolean-detection and other-location branches from the per-step detection code (which
 // is ~45 % of the instructions of the bouncing-ball run in the generic profile).
-template <class Sys, int S_, int I_, unsigned long long AMASK, unsigned BMASK, bool FAST, int NLOC, bool SIMPLE = false>
+// LEAN = no Trace policy on this problem (known at launch): the per-step `on_step` test disappears.
+template <class Sys, int S_, int I_, unsigned long long AMASK, unsigned BMASK, bool FAST, int NLOC, bool SIMPLE = false,
+          bool LEAN = false>
 struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
   using Base = OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1>;
   static constexpr int S = S_, I = I_;
@@ -69,9 +71,19 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
 
   size_t gid;
   double aux[NA];
-  // FAST: the pre-combined interpolant of the parked step overwrites k[1 .. I-1] (the stages are
-  // dead once a lane is parked: the event re-step recomputes them and only k[0] = d_prev is needed
-  // for the undo), so parking adds no loop-carried registers
+  // FAST: a lane that detects an event pre-combines the step's interpolant into `cf` and saves d_prev
+  // AT ONCE, inside the (rare) fired branch.  The stage vectors k[][] are then dead at the end of every
+  // loop iteration, and `cf` / `dprev` are untouched on the event-free path — so the loop back-edge
+  // carries no copies of them.  (Round 1 pre-combined lazily in the locate round, which kept all of
+  // k[][] live around the loop: ~45 register moves per step, 24 % of the executed instructions.)
+  // STRICT evaluates the reference's dense_output on k[][] itself and keeps it live.
+  // Narrow states only (N <= 2: the bouncing ball): for N = 4 the extra 2 (I-1) N registers cost more than
+  // the moves they save (egg billiard 15.7 -> 16.7 ms), so wide states keep round 1's scheme — coefficients
+  // overwrite k[1 .. I-1], pre-combined lazily in the locate round.
+  static constexpr bool EAGER = FAST && Sys::N <= 2;
+  static constexpr int NCF = I_ > 1 ? I_ - 1 : 1;
+  double cf[EAGER ? NCF : 1][EAGER ? N : 1];
+  double dprev[EAGER ? N : 1];
   double last_call[NLOC], sep_prev[NLOC];
   int every_i[NLOC];
   uint32_t has_last_call, status;
@@ -85,20 +97,22 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
   __device__ __forceinline__ Ref view_curr() {
     return Ref{t_curr, p_curr(), d_curr(), t_prev, p_prev(), &this->nohist};
   }
-  __device__ __forceinline__ Ref view_prev() {  // state_fn.rs:181-188; d_prev is still in k[0]
-    return Ref{t_prev, p_prev(), k()[0], t_prev, p_prev(), &this->nohist};
+  // state_fn.rs:181-188.  The view's `d` is d_prev: k[0] after a step (STRICT), the copy a parked lane saved
+  // (FAST).  No functor this kernel takes reads it (static_assert above), so only its type matters.
+  __device__ __forceinline__ Ref view_prev() {
+    return Ref{t_prev, p_prev(), EAGER ? dprev : k()[0], t_prev, p_prev(), &this->nohist};
   }
 
   // ---- interpolant of the step in flight (State::eval, state.rs:83-92) ------------------
   __device__ __forceinline__ void precombine() {
     if (!FAST) return;
-    static_assert(!FAST || I <= S, "the interpolant coefficients are stored in k[1 .. I-1]");
+    static_assert(!FAST || EAGER || I <= S, "the interpolant coefficients are stored in k[1 .. I-1]");
     // y(t) = p_prev + sum_j c_j (t - t_prev)^j with c_j = h sum_i k_i bi[i][j] / h^j: the division
     // theta = (t - t_prev) / h of rk.rs/state.rs:85 is paid once per event, not once per iteration
     const double t_step = t_curr - t_prev;
     const double inv = 1.0 / t_step;
     double scale = 1.0;  // h / h^j
-    double c[I > 1 ? I - 1 : 1][N];
+    double c[NCF][N];
 #pragma unroll
     for (int j = 1; j < I; ++j) {
 #pragma unroll
@@ -113,9 +127,16 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
 #pragma unroll
     for (int j = 1; j < I; ++j)
 #pragma unroll
-      for (int n = 0; n < N; ++n) k()[j][n] = c[j - 1][n];
+      for (int n = 0; n < N; ++n) {
+        if (EAGER) cf[EAGER ? j - 1 : 0][EAGER ? n : 0] = c[j - 1][n];
+        else k()[j][n] = c[j - 1][n];
+      }
+    if (EAGER) {
+#pragma unroll
+      for (int n = 0; n < N; ++n) dprev[EAGER ? n : 0] = k()[0][n];
+    }
   }
-  __device__ __forceinline__ double cj(int j, int n) { return k()[j + 1][n]; }
+  __device__ __forceinline__ double cj(int j, int n) { return EAGER ? cf[EAGER ? j : 0][EAGER ? n : 0] : k()[j + 1][n]; }
   template <int D>
   __device__ __forceinline__ void eval_in_step(double t, double* out) {
     if (FAST && D == 0) {
@@ -286,6 +307,26 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
     return true;
   }
 
+  // SIMPLE profile: every locator's detection (DedupLocF loc.rs:1002-1011 around a sign-change detection
+  // loc.rs:127-135) as straight-line predicate arithmetic — no early outs, so no branches: a taken branch
+  // costs this kernel ~15 issue cycles with 4 warps per scheduler, and round 1 had ~8 per step here
+  __device__ __forceinline__ unsigned detect_all_simple() {
+    unsigned fired = 0u;
+#pragma unroll
+    for (int l = 0; l < NLOC; ++l) {
+      const dfb_locator& L = A.loc[l];
+      const double c = Sys::detector(L.detector_id, view_curr(), prm());
+      const double p = Sys::detector(L.detector_id, view_prev(), prm());
+      const bool up = (c > 0.0) & (p <= 0.0);      // AboveZero (loc.rs:130-132)
+      const bool down_z = (c <= 0.0) & (p > 0.0);  // the falling half of Zero (loc.rs:127-129)
+      const bool down = (c < 0.0) & (p >= 0.0);    // BelowZero (loc.rs:133-135)
+      const bool det = L.detection == DFB_DET_ZERO ? (up | down_z) : (L.detection == DFB_DET_ABOVE_ZERO ? up : down);
+      const bool suppressed = (L.dedup != 0) & (((has_last_call >> l) & 1u) != 0u) & !(t_prev > last_call[l]);
+      fired |= ((l < A.n_loc) & det & !suppressed) ? (1u << l) : 0u;
+    }
+    return fired;
+  }
+
   // DedupLocF (loc.rs:1002-1011) + filter wrappers (FilterAfterDetection :484-486, FilterLocated :568-576)
   __device__ __forceinline__ bool detect_phase(const dfb_locator& L, int l) {
     if (L.dedup && ((has_last_call >> l) & 1u) && !(t_prev > last_call[l])) return false;
@@ -302,6 +343,7 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
 
   // output policy standing in for on_step closures (solver.rs:290, 309)
   __device__ __forceinline__ void on_step() {
+    if (LEAN) return;
     if (A.trace_every > 0) {
       if (on_step_calls % (unsigned long long)A.trace_every == 0 && n_samples < uint32_t(A.trace_capacity)) {
         const size_t n_traj = A.n_traj;
@@ -435,7 +477,7 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
 #pragma unroll
             for (int n = 0; n < N; ++n) {
               p_curr()[n] = p_prev()[n];
-              d_curr()[n] = k()[0][n];
+              d_curr()[n] = EAGER ? dprev[EAGER ? n : 0] : k()[0][n];
             }
             ev_time = best_t;
             ev_index = best_i;
@@ -504,11 +546,19 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
               on_step();
               mode = next_mode();
             } else {
-              fired_mask = 0u;
+              if (SIMPLE) {
+                fired_mask = detect_all_simple();
+              } else {
+                fired_mask = 0u;
 #pragma unroll
-              for (int l = 0; l < NLOC; ++l)
-                if (l < A.n_loc && detect_phase(A.loc[l], l)) fired_mask |= 1u << l;
+                for (int l = 0; l < NLOC; ++l)
+                  if (l < A.n_loc && detect_phase(A.loc[l], l)) fired_mask |= 1u << l;
+              }
               if (fired_mask != 0u) {
+                if (EAGER && !combined) {  // park with the interpolant and d_prev in hand: k[][] dies here
+                  precombine();
+                  combined = true;
+                }
                 mode = MODE_LOCATE;
               } else {
                 ++n_steps;  // commit_step
@@ -527,10 +577,10 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
 #define DFB_EV_MINB(N) ((N) <= 2 ? 4 : 3)
 #endif
 template <class Sys, int S, int I, unsigned long long AMASK, unsigned BMASK, bool FAST, int NLOC, int BLOCK,
-          bool SIMPLE = false>
+          bool SIMPLE = false, bool LEAN = false>
 __global__ void __launch_bounds__(BLOCK, DFB_EV_MINB(Sys::N))
     ode_event_kernel(const __grid_constant__ OdeFixedArgs A) {
-  OdeEventStepper<Sys, S, I, AMASK, BMASK, FAST, NLOC, SIMPLE> st(A);
+  OdeEventStepper<Sys, S, I, AMASK, BMASK, FAST, NLOC, SIMPLE, LEAN> st(A);
   st.run();
 }
 

@@ -35,13 +35,16 @@ bool try_launch(int S_rt, int I_rt, const OdeFixedArgs& A, int n_sm, cudaStream_
              (L.detection == DFB_DET_ZERO || L.detection == DFB_DET_ABOVE_ZERO || L.detection == DFB_DET_BELOW_ZERO);
   }
   if constexpr (S == 7) {
+    const bool lean = A.trace_every == 0 && !getenv("DFB_EVENT_NO_LEAN");  // no Trace policy: LEAN build
     if (simple && A.n_loc <= 1) {
-      launch_grid(ode_event_kernel<Sys, S, I, AM, BM, kFast, 1, kBlock, true>, A, n_sm, stream);
+      if (lean) launch_grid(ode_event_kernel<Sys, S, I, AM, BM, kFast, 1, kBlock, true, true>, A, n_sm, stream);
+      else launch_grid(ode_event_kernel<Sys, S, I, AM, BM, kFast, 1, kBlock, true>, A, n_sm, stream);
       *rc = int(cudaGetLastError());
       return true;
     }
     if (simple && A.n_loc == 2) {
-      launch_grid(ode_event_kernel<Sys, S, I, AM, BM, kFast, 2, kBlock, true>, A, n_sm, stream);
+      if (lean) launch_grid(ode_event_kernel<Sys, S, I, AM, BM, kFast, 2, kBlock, true, true>, A, n_sm, stream);
+      else launch_grid(ode_event_kernel<Sys, S, I, AM, BM, kFast, 2, kBlock, true>, A, n_sm, stream);
       *rc = int(cudaGetLastError());
       return true;
     }

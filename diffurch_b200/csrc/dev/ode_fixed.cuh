@@ -430,8 +430,9 @@ struct OdeFixedPeriodicStepper : OdeFixedStepper<Sys, S, AMASK, BMASK, PRESCALED
 template <class Sys, int S, unsigned long long AMASK, unsigned BMASK, bool PRESCALED, int BLOCK, int TPT, int MINB = 1>
 __global__ void __launch_bounds__(BLOCK, MINB)
     ode_fixed_periodic_kernel(const __grid_constant__ OdeFixedArgs A) {
-  const size_t g = size_t(blockIdx.x) * BLOCK + threadIdx.x;
-  const size_t stride = size_t(gridDim.x) * BLOCK;
+  // BLOCK is the launch bound; the host sizes the block (<= BLOCK) from the ensemble (host/launch_geometry.hpp)
+  const size_t g = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
   size_t gid[TPT];
   bool valid[TPT];
 #pragma unroll

@@ -108,27 +108,42 @@ bool try_launch_periodic(int S_rt, unsigned long long amask, unsigned bmask, con
                          cudaStream_t stream, int* rc) {
   if (S_rt != S) return false;
   if ((amask & ~AMASK) != 0ull || (bmask & ~BMASK) != 0u) return false;
-  const size_t grid = (A.n_traj + kBlock - 1) / kBlock;
   // Wide states (the 12-component Lyapunov system) take 218 registers uncapped: 8 resident warps
   // per SM, latency-bound (ncu: FP64 pipe 75 % active, 0.7 eligible warps per cycle).  Capped at 200
   // registers in 64-thread blocks (10 warps) the pipe saturates: 216.6 -> 208.9 ms on the 2^18-member
   // Lorenz spectrum batch; 168 registers (12 warps) gives the same time.  DFB_PERIODIC_MINB=1|3|5|6
-  // selects the build (tuning).
+  // selects the build (tuning).  The block itself (<= the launch bound) is sized from the ensemble so that a
+  // shard of the batch (2^18 members over 8 GPUs = 1 024 warps for 148 SMs) spreads evenly over the SMs.
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  auto pick = [&](int max_block) {
+    dfb_host::GeometryCandidate cand[3];
+    int nc = 0;
+    for (int b : {128, 64, 32})
+      if (b <= max_block) cand[nc++] = {b, 1, 0, 1.0};
+    return dfb_host::choose_geometry(A.n_traj, n_sm, cand, nc);
+  };
   bool wide = false;
   if constexpr (Sys::N >= 8) {
     const char* e = getenv("DFB_PERIODIC_MINB");
     const int m = e ? atoi(e) : 5;
     wide = m == 3 || m == 5 || m == 6;
-    const size_t grid64 = (A.n_traj + 63) / 64;
+    const auto g128 = pick(128), g64 = pick(64);
     if (m == 3)
-      ode_fixed_periodic_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 1, 3><<<unsigned(grid), kBlock, 0, stream>>>(A);
+      ode_fixed_periodic_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 1, 3><<<unsigned(g128.grid), g128.block, 0, stream>>>(A);
     else if (m == 5)
-      ode_fixed_periodic_kernel<Sys, S, AMASK, BMASK, kPrescaled, 64, 1, 5><<<unsigned(grid64), 64, 0, stream>>>(A);
+      ode_fixed_periodic_kernel<Sys, S, AMASK, BMASK, kPrescaled, 64, 1, 5><<<unsigned(g64.grid), g64.block, 0, stream>>>(A);
     else if (m == 6)
-      ode_fixed_periodic_kernel<Sys, S, AMASK, BMASK, kPrescaled, 64, 1, 6><<<unsigned(grid64), 64, 0, stream>>>(A);
+      ode_fixed_periodic_kernel<Sys, S, AMASK, BMASK, kPrescaled, 64, 1, 6><<<unsigned(g64.grid), g64.block, 0, stream>>>(A);
   }
-  if (!wide)
-    ode_fixed_periodic_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 1><<<unsigned(grid), kBlock, 0, stream>>>(A);
+  if (!wide) {
+    const auto g = pick(128);
+    ode_fixed_periodic_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 1><<<unsigned(g.grid), g.block, 0, stream>>>(A);
+  }
   *rc = int(cudaGetLastError());
   return true;
 }

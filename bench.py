@@ -22,7 +22,7 @@ full-size shard; under the default a short weak-scaling pass is also run and rep
 
 `--impl reference` times the reference's CPU path.  The Rust crate cannot be built in this image (no
 cargo/rustc, un-vendored git dependency), so that arm runs the C++ restatement under oracle/ (kind
-"port", built -O2 -ffp-contract=off) on all host cores, on a bounded sample of the same workload.
+"port", built -O3 -ffp-contract=off) on all host cores, on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -178,7 +178,7 @@ def sized_cpu_baseline(rate_fn, steps_per_member, cores, seconds, label):
     rate1, _, _ = rate_fn(8, 1)
     return {"value": rate, "unit": "RK steps/s", "cores": cores, "kind": "port",
             "sample": f"{n_sample} members x {steps_per_member} steps of {label} ({dt:.1f} s), C++ restatement of the "
-                      f"reference CPU path built -O2 -ffp-contract=off (Rust toolchain unavailable), std::thread "
+                      f"reference CPU path built -O3 -ffp-contract=off (Rust toolchain unavailable), std::thread "
                       f"over members, one Solver per member",
             "single_core_ns_per_step": 1e9 / rate1}
 
@@ -197,7 +197,7 @@ def run_reference(args, rank, world):
         times.append(dt)
     value = float(np.mean(rates))
     sample = (f"{n_sample} of the 2^20 members per step (same rho sweep end points, same t range), "
-              f"{cores} std::thread workers, one Solver per member; oracle built -O2 -ffp-contract=off")
+              f"{cores} std::thread workers, one Solver per member; oracle built -O3 -ffp-contract=off")
     cpu = {"value": value, "unit": "RK steps/s", "cores": cores, "kind": "port", "sample": sample}
     if not os.environ.get("DFB_BENCH_SKIP_DDE"):
         n_dde = max(cores, int(os.environ.get("DFB_BENCH_REF_SAMPLE", 4096 * cores)) // 4)

@@ -1063,6 +1063,20 @@ def test_full_size_lorenz_properties():
     assert np.array_equal(again.p, g.p)                               # deterministic
 
 
+def test_full_size_lorenz_strict_subsample_is_bit_exact_at_t50(oracle):
+    # the same 2^20-member launch in STRICT arithmetic, and 64 members spread over the sweep re-integrated
+    # by the CPU oracle to t = 50 (12 501 steps): STRICT is the reference's rounding, so chaos is no excuse —
+    # every sampled member must agree to the last bit at full size, wherever it sat in the grid
+    n = 1 << 20
+    rho = 20.0 + 20.0 * np.arange(n) / (n - 1)
+    g = cases.lorenz(n=n, t1=50.0, arith="strict", rho=rho).run()
+    assert g.totals["kernel_kind"] == KERNEL_ODE_FIXED and np.all(g.status == 0) and np.all(g.steps == 12501)
+    idx = np.unique(np.concatenate([np.linspace(0, n - 1, 60).astype(np.int64), [1, 31, 32, n - 2]]))
+    o = oracle.run_solver(cases.lorenz(n=len(idx), t1=50.0, arith="strict", rho=rho[idx]), n_threads=8)
+    assert np.array_equal(g.p[idx], o.p) and np.array_equal(g.t[idx], o.t)
+    assert np.array_equal(g.steps[idx], o.steps) and np.array_equal(g.rhs_evals[idx], o.rhs_evals)
+
+
 def test_full_size_linearity_property():
     # y' = A y is linear: scaling y0 by a power of two scales the result exactly, in both arithmetics
     n = 1 << 18

@@ -323,6 +323,23 @@ def test_fuzz_dde_events_and_propagation_strict_bit_exact(oracle, seed):
     o = oracle.run_solver(mk(), n_threads=4)
     SEEN.add(g.totals["kernel_kind"])
     same(g, o, what)
+    # the same problem in FAST arithmetic: dde_event_kernel where a (system, tableau shape) instantiation
+    # exists, the general kernel otherwise.  y' = 0 makes the time grid pure time arithmetic (FAST = STRICT
+    # bit for bit); the relay-clamp DDE must keep the event sequence and stay within the FAST tolerances
+    f = mk().arith("fast").run()
+    SEEN.add(f.totals["kernel_kind"])
+    compiled = ("rk4", "euler") if "zero1" in what else ("rktp64", "rk4")   # kernels_dde_event.cu shape_compiled
+    if rk_name in compiled:
+        assert f.totals["kernel_kind"] == abi.KERNEL_DDE_EVENT, what
+    if "zero1" in what:
+        same(f, o, what + " fast")
+    else:
+        assert np.array_equal(f.status, o.status), what
+        ok = o.status == 0
+        assert np.array_equal(f.steps[ok], o.steps[ok]) and np.array_equal(f.events[ok], o.events[ok]), what
+        assert np.array_equal(f.event_n[ok], o.event_n[ok]) and np.array_equal(f.event_index[ok], o.event_index[ok]), what
+        assert np.allclose(f.event_t[ok], o.event_t[ok], rtol=0.0, atol=1e-9, equal_nan=True), what
+        assert np.allclose(f.p[ok], o.p[ok], rtol=1e-8, atol=1e-8), what
 
 
 @pytest.mark.parametrize("seed", range(10 * SCALE))
@@ -469,4 +486,4 @@ def test_fuzz_reached_every_ode_kernel_family():
     if not SEEN:
         pytest.skip("fuzz cases did not run in this session")
     assert {abi.KERNEL_ODE_FIXED, abi.KERNEL_ODE_EVENT, abi.KERNEL_GENERAL, abi.KERNEL_ODE_ADAPTIVE,
-            abi.KERNEL_DDE_FIXED}.issubset(SEEN), SEEN
+            abi.KERNEL_DDE_FIXED, abi.KERNEL_DDE_EVENT}.issubset(SEEN), SEEN

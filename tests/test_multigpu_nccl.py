@@ -87,6 +87,25 @@ def test_two_gpu_sharded_run_and_nccl_gather(tmp_path):
     assert np.array_equal(got["y_all"], one.p) and np.array_equal(got["t_all"], one.t)
 
 
+@pytest.mark.gpu
+def test_one_rank_nccl_gather_runs_the_products_allgather(tmp_path):
+    # The same worker with a ONE-rank communicator: `dfb_gather_final` still packs (t, y), calls
+    # ncclAllGather on the library's own buffers and unpacks — so the product's NCCL path is exercised on a
+    # one-GPU box too (the two-rank tests below need `gpurun --gpus 2`).
+    import torch.multiprocessing as mp
+    import diffurch_b200 as d
+    n = 777
+    out = str(tmp_path / "g1.npz")
+    mp.spawn(_worker, args=(1, _free_port(), n, out), nprocs=1, join=True)
+    got = np.load(out)
+    rho = 20.0 + 20.0 * np.arange(n) / (n - 1)
+    prm = np.stack([np.full(n, 10.0), rho, np.full(n, 8.0 / 3.0)], axis=1)
+    one = (d.Solver.new().initial(np.tile([1., 2., 20.], (n, 1))).equation(d.systems.Lorenz, prm)
+           .interval(0.0, 2.0).stepsize(1.0 / 250.0).run())
+    assert np.array_equal(got["y_all"], one.p) and np.array_equal(got["t_all"], one.t)
+    assert np.array_equal(got["p"], one.p)
+
+
 def _lyap_worker(rank, world, port, n, tmax, out_path):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))

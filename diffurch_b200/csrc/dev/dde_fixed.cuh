@@ -130,7 +130,32 @@ struct WindowHist {
   }
 };
 
-template <class Sys, int S, int I, unsigned long long AMASK, unsigned BMASK, unsigned long long BIMASK>
+// PRE: the delayed values of a whole steady step, evaluated BEFORE its stage chain.  With a constant delay
+// the lookup times of a step, t_prev + c_i h - tau, do not depend on the state, so the S Horner chains are
+// independent of each other and of the stages; taken out of the right-hand sides they run with ILP S, and the
+// dependent chain of the step (stage sum -> rhs -> stage sum ...) is 2-3 FP64 latencies per stage instead of
+// a staged-memory load + 4 dependent FMAs + 2-3.  That is what a LONE warp needs (a shard of the ensemble:
+// 1-2 warps per SM sub-partition, nothing else hides the latency); a full device is issue-bound and does not
+// care.  The functor still calls s.p_at(s.t - tau): the view's history hands back the value computed for that
+// very time (same expression, same bits) and falls back to the window for any other.
+template <class Stepper>
+struct PreHist {
+  Stepper* st;
+  int i;  // stage slot (compile-time after unrolling)
+  template <int D>
+  __device__ __forceinline__ void eval(double tt, double* out) {
+    constexpr int N = Stepper::N;
+    if (tt == st->pre_t[i]) {
+#pragma unroll
+      for (int n = 0; n < N; ++n) out[n] = D == 0 ? st->pre_p[i][n] : st->pre_d[i][n];
+    } else {
+      WindowHist<Stepper, true> w{st};
+      w.template eval<D>(tt, out);
+    }
+  }
+};
+
+template <class Sys, int S, int I, unsigned long long AMASK, unsigned BMASK, unsigned long long BIMASK, bool PRE = false>
 struct DdeFixedStepper {
   using SysT = Sys;
   using Self = DdeFixedStepper;
@@ -161,6 +186,8 @@ struct DdeFixedStepper {
   uint32_t n_samples = 0u, n_samples_alive = 0u;
   bool loaded, uniform;
   bool track_oldest;  // max_delay < tau: "deleted time range" panics (state.rs:166-171) are possible
+  double tau_;        // this lane's delay (PRE)
+  double pre_t[PRE ? S : 1], pre_p[PRE ? S : 1][N], pre_d[PRE ? S : 1][N];  // slot i-1 = stage i, slot S-1 = step end
   unsigned warp_base, slot_stride;  // ring addressing in doubles: [slot][warp][F][32] (host guarantees < 2^32)
 
   __device__ DdeFixedStepper(const DdeFixedArgs& A_, size_t g_, size_t gid_, bool valid_, double* sm_)
@@ -170,6 +197,10 @@ struct DdeFixedStepper {
   __device__ __forceinline__ void rhs(double* out) {
     WindowHist<Self, STEADY> h{this};
     Sys::rhs(StateRef<N, WindowHist<Self, STEADY>>{t_curr, p_curr, d_curr, t_prev, p_prev, &h}, prm, out);
+  }
+  __device__ __forceinline__ void rhs_pre(int slot, double* out) {
+    PreHist<Self> h{this, slot};
+    Sys::rhs(StateRef<N, PreHist<Self>>{t_curr, p_curr, d_curr, t_prev, p_prev, &h}, prm, out);
   }
 
   __device__ __forceinline__ static bool amask(int i, int j) { return (AMASK >> (i * 8 + j)) & 1ull; }
@@ -182,6 +213,17 @@ struct DdeFixedStepper {
       p_prev[n] = p_curr[n];
     }
     t_prev = t_curr;
+    constexpr bool kPre = PRE && FULL && STEADY;
+    if (kPre) {
+      WindowHist<Self, true> w{this};
+#pragma unroll
+      for (int i = 1; i <= S; ++i) {
+        const double tt = (t_prev + (i < S ? A.hc[i] : t_step)) - tau_;
+        pre_t[kPre ? i - 1 : 0] = tt;
+        w.template eval<0>(tt, pre_p[kPre ? i - 1 : 0]);
+        w.template eval<1>(tt, pre_d[kPre ? i - 1 : 0]);  // dead code unless the functor asks for y'(t - tau)
+      }
+    }
 #pragma unroll
     for (int i = 1; i < S; ++i) {
       t_curr = t_prev + (FULL ? A.hc[i] : A.c[i] * t_step);
@@ -201,7 +243,8 @@ struct DdeFixedStepper {
           p_curr[n] = fma(acc, t_step, p_prev[n]);
         }
       }
-      rhs<STEADY>(k[i]);
+      if (kPre) rhs_pre(i - 1, k[i]);
+      else rhs<STEADY>(k[i]);
     }
 #pragma unroll
     for (int n = 0; n < N; ++n) {
@@ -220,7 +263,8 @@ struct DdeFixedStepper {
       }
     }
     t_curr = t_prev + t_step;
-    rhs<STEADY>(d_curr);
+    if (kPre) rhs_pre(S - 1, d_curr);
+    else rhs<STEADY>(d_curr);
   }
 
   // ---- ring I/O: [slot][warp][field][lane] -----------------------------------
@@ -358,6 +402,7 @@ struct DdeFixedStepper {
 #pragma unroll
     for (int n = 0; n < Sys::NP; ++n) prm[n] = A.params[size_t(n) * n_traj + gid];
     const double tau = Sys::const_delay(prm);
+    tau_ = tau;
     // the staged (warp-cooperative) path needs one window position per warp
     uniform = __all_sync(0xffffffffu, __double_as_longlong(tau) ==
                                           __shfl_sync(0xffffffffu, __double_as_longlong(tau), 0));
@@ -453,10 +498,10 @@ struct DdeFixedStepper {
 };
 
 template <class Sys, int S, int I, unsigned long long AMASK, unsigned BMASK, unsigned long long BIMASK,
-          int BLOCK, int MIN_BLOCKS>
+          int BLOCK, int MIN_BLOCKS, bool PRE = false>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
     dde_fixed_kernel(const __grid_constant__ DdeFixedArgs A) {
-  using Stepper = DdeFixedStepper<Sys, S, I, AMASK, BMASK, BIMASK>;
+  using Stepper = DdeFixedStepper<Sys, S, I, AMASK, BMASK, BIMASK, PRE>;
   // (blockDim.x / 32) * kDdeSmemSlots * kWarpRec doubles, sized by the launcher: BLOCK is the launch
   // bound, the block itself is chosen from the ensemble size (host/launch_geometry.hpp)
   extern __shared__ __align__(16) double smem[];

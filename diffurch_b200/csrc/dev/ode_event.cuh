@@ -25,6 +25,9 @@
 //  * dynamic trajectory assignment (global work counter) as in ode_adaptive.cuh: members stop at
 //    different times (egg billiard: after 200 reflections), finished lanes pull the next member.
 #pragma once
+#ifndef DFB_EV_EAGER_MAX_N
+#define DFB_EV_EAGER_MAX_N 2
+#endif
 #ifndef DFB_EV_UNROLL
 #define DFB_EV_UNROLL 1
 #endif
@@ -80,7 +83,7 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
   // Narrow states only (N <= 2: the bouncing ball): for N = 4 the extra 2 (I-1) N registers cost more than
   // the moves they save (egg billiard 15.7 -> 16.7 ms), so wide states keep round 1's scheme — coefficients
   // overwrite k[1 .. I-1], pre-combined lazily in the locate round.
-  static constexpr bool EAGER = FAST && Sys::N <= 2;
+  static constexpr bool EAGER = FAST && Sys::N <= DFB_EV_EAGER_MAX_N;
   static constexpr int NCF = I_ > 1 ? I_ - 1 : 1;
   double cf[EAGER ? NCF : 1][EAGER ? N : 1];
   double dprev[EAGER ? N : 1];
@@ -455,8 +458,10 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
       if (locate_round) {
         parked_iters = 0;
         if (mode == MODE_LOCATE) {
-          if (!combined) precombine();
-          combined = true;
+          if (!EAGER) {  // EAGER lanes combined when they parked; a call here would keep k[][] live around the loop
+            if (!combined) precombine();
+            combined = true;
+          }
           bool found = false;
           double best_t = 0.0;
           int best_i = 0;

@@ -383,6 +383,31 @@ struct DdeFixedStepper {
     // next step's t_prev, so only lookups the reference rejects as "not yet computed" select it.
   }
 
+  // refill for the steady regime of a warp-uniform delay (every record the window fetches is at least three
+  // steps older than the one just committed, no prune replay): the same window rule as refill() without its
+  // start-up, short-delay and per-lane branches.  Anything else goes through refill().
+  __device__ __forceinline__ void refill_steady(int s, double tau, double h) {
+    if (!(uniform && !track_oldest && loaded && w + 4 < s)) {
+      refill(s, tau, h);
+      return;
+    }
+    const double next_len = fmin(h, A.t1 - t_curr);
+    const double tt_min = (t_curr + (next_len == h ? A.hc_min : A.c_min * next_len)) - tau;
+    int r = w + 3;  // records <= w + 2 were issued by earlier refills
+    while (tw1 <= tt_min) {
+      ++w;
+      tw0 = tw1;
+      tw1 = tw1 + h;
+    }
+#pragma unroll 1
+    for (; r <= w + 2 && r <= s; ++r) issue_fetch(r);
+    cp_async_commit();
+    cp_async_wait<1>();  // record w + 1 was issued one refill ago at the latest
+    __syncwarp();
+    p0 = smem_block(w) + lane;
+    p1 = smem_block(w + 1) + lane;
+  }
+
   // every trace_every-th on_step invocation stores (t, p); the grid is shared, the test is uniform
   __device__ __forceinline__ void on_step(unsigned calls) {
     if (A.trace_every > 0 && calls % unsigned(A.trace_every) == 0u && n_samples < uint32_t(A.trace_capacity)) {
@@ -466,7 +491,7 @@ struct DdeFixedStepper {
         if (track_oldest && (t_curr + A.hc_min) - tau < t_oldest) status |= DFB_TRAJ_HISTORY_DELETED;
         step<true, true>(h);
         commit<true>(s, h);
-        refill(s, tau, h);
+        refill_steady(s, tau, h);
         ++s;
         on_step(unsigned(s));
       }

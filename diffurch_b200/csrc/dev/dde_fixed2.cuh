@@ -245,6 +245,29 @@ struct DdeFixedStepperT {
     p1 = smem_block(w + 1) + lane;
   }
 
+  // refill for the steady regime (see DdeFixedStepper::refill_steady)
+  __device__ __forceinline__ void refill_steady(int s, double tau, double h) {
+    if (!(!track_oldest && loaded && w + 4 < s)) {
+      refill(s, tau, h);
+      return;
+    }
+    const double next_len = fmin(h, A.t1 - t_curr);
+    const double tt_min = (t_curr + (next_len == h ? A.hc_min : A.c_min * next_len)) - tau;
+    int r = w + 3;
+    while (tw1 <= tt_min) {
+      ++w;
+      tw0 = tw1;
+      tw1 = tw1 + h;
+    }
+#pragma unroll 1
+    for (; r <= w + 2 && r <= s; ++r) issue_fetch(r);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    p0 = smem_block(w) + lane;
+    p1 = smem_block(w + 1) + lane;
+  }
+
   // gid_[u] / valid_[u] / g_[u] (global thread slot index) set by the kernel; tau is the warp's delay
   __device__ void run(double tau) {
     const size_t n_traj = A.n_traj;
@@ -303,7 +326,7 @@ struct DdeFixedStepperT {
         }
         step<true, true>(h);
         commit<true>(s, h);
-        refill(s, tau, h);
+        refill_steady(s, tau, h);
         ++s;
         on_step(unsigned(s));
       }

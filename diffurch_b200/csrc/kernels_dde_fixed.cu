@@ -59,7 +59,9 @@ bool try_launch(int S_rt, int I_rt, unsigned long long am, unsigned bm, unsigned
                          int((kBlock / 32) * kDdeSmemSlots * Stepper::kWarpRec * sizeof(double)));
   }
   const size_t warps = (A.n_traj + 31) / 32;
-  int tpt = A.n_traj >= 65536 ? 2 : 1;
+  // two members per thread pay once ~20 warps per SM exist (measured: 2^16 members 5.18 ms one per
+  // thread vs 5.34 two per thread; 2^17 members 9.45 vs 9.32)
+  int tpt = warps >= size_t(n_sm) * 20 ? 2 : 1;
   // below ~16 warps per SM one warp per block spreads the ensemble over every SM sub-partition
   int block = warps >= size_t(n_sm) * 16 ? kBlock : (warps >= size_t(n_sm) * 8 ? 64 : 32);
   if (const char* e = getenv("DFB_DDE_TPT")) tpt = atoi(e) == 2 ? 2 : 1;
@@ -74,7 +76,8 @@ bool try_launch(int S_rt, int I_rt, unsigned long long am, unsigned bm, unsigned
     // Few warps per SM (a shard of the ensemble): nothing hides the latency of a warp's own instruction
     // stream, so the build WITHOUT the 72-register cap runs — the scheduler may then hoist the step's
     // state-independent history evaluations above the dependent stage chain.  DFB_DDE_RELAXED=0|1 overrides.
-    bool relaxed = warps < size_t(n_sm) * 12;
+    // Measured faster at every size the one-member kernel is chosen for (2^16: 5.18 vs 5.58 ms).
+    bool relaxed = true;
     if (const char* e = getenv("DFB_DDE_RELAXED")) relaxed = atoi(e) != 0;
     if (relaxed) {
       auto kernel1r = dde_fixed_kernel<Sys, S, I, AMASK, BMASK, BIMASK, kBlock, 2, true>;

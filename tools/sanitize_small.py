@@ -24,7 +24,24 @@ runs = {
     "general: dde strict": lambda: cases.eq_dde_sin(k=0.5 + np.arange(70) / 69.0, trace=False),
     "general: dde relay clamp (propagation + events)": lambda: cases.dde_relay_clamp(t1=3.0),
     "general: adaptive + trace": lambda: cases.lorenz(n=50, t1=0.5).stepsize(auto).on_step(d.Trace(1, 256)),
+    "dde_event: relay clamp ensemble (ragged 333, events + propagation)":
+        lambda: cases.dde_relay_clamp_ensemble(333, arith="fast", t1=6.0, events=64, trace=d.Trace(5, 128)),
+    "dde_event: relay clamp, small ring (overflow path)":
+        lambda: cases.dde_relay_clamp_ensemble(40, arith="fast", t1=4.0, events=16).ring_capacity(64),
+    "dde_event: propagated delays, euler (tests/delay_propagation.rs)": lambda: cases.delay_constant_2().arith("fast"),
+    "dde_event: pantograph, unbounded max_delay": lambda: cases.delay_pantograph().arith("fast"),
+    "dde_event: plain DDE + max_steps": lambda: cases.eq_dde_sin(k=0.5 + np.arange(40) / 39.0, t1=3.0, arith="fast").max_steps(100000),
+    "dde_fixed PRE build (small shard)": lambda: cases.eq_dde_sin(k=0.5 + np.arange(2000) / 1999.0, t1=3.0, trace=False).arith("fast"),
 }
+from diffurch_b200 import user  # noqa: E402
+vdp = user.load_user_system_from_source(os.path.join(ROOT, "tests", "plugins", "van_der_pol.cuh"), "SysVanDerPol",
+                                        params=("mu",), detectors={"x": 1}, callbacks={"count": 1})
+mu = np.linspace(0.3, 3.0, 77).reshape(-1, 1)
+runs["nvrtc: ode_fixed (source system)"] = lambda: (d.Solver.new().initial(np.tile([2.0, 0.0], (77, 1))).equation(vdp, mu)
+                                                    .interval(0.0, 1.0).stepsize(0.01).arith("fast"))
+runs["nvrtc: general (events)"] = lambda: (d.Solver.new().initial(np.tile([2.0, 0.0], (77, 1))).equation(vdp, mu)
+                                           .interval(0.0, 4.0).stepsize(0.01).arith("strict")
+                                           .on_mut(d.Locator.zero("x"), "count"))
 for name, mk in runs.items():
     r = mk().run()
     print(f"{name:50s} kernel_kind={r.totals['kernel_kind']} steps={int(r.steps.sum())} failed={r.totals['n_failed']}")

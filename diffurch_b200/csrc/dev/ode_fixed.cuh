@@ -15,6 +15,10 @@
 #include "common.cuh"
 #include "systems.cuh"
 
+#ifndef DFB_ODE_FOLD_MIN_N
+#define DFB_ODE_FOLD_MIN_N 8
+#endif
+
 namespace DFB_NS {
 
 // history stub for ODE right-hand sides (they never call p(t)/d(t))
@@ -102,8 +106,109 @@ struct OdeFixedStepper {
 
   // One make_step of length t_step; FULL = (t_step == A.h), the only case the
   // pre-scaled rows are valid for.
+  // Wide states (N * TPT >= DFB_ODE_FOLD_MIN_N doubles per stage vector) do not keep all S stage
+  // derivatives: after k[0 .. M-1], M = ceil(S/2), every later row of the tableau (and the b row) is
+  // opened as a running sum over those, and each later derivative is folded into the rows that still
+  // need it the moment the right-hand side returns it.  Same operations in the same order per
+  // element as the plain form below (bit-identical, STRICT included) — only their position in time
+  // changes: at most ~S/2 + 1 stage vectors are live instead of S + 1 (N = 12, rktp64: 218 -> ~150
+  // registers).  Nothing after the step reads k[1 .. S-1] in the kernels that use this stepper.
+  static constexpr bool FOLD = (N * TPT >= DFB_ODE_FOLD_MIN_N) && S >= 4;
+
+  // FMA form of a folded step: PRESCALED builds (FAST) run every row as acc = fma(k, coef, acc) starting
+  // from p_prev — full steps with the pre-scaled rows h a_ij / h b_j, any other step length (the step to
+  // an event time, the last step of the interval) with the derivatives scaled by t_step as they are
+  // produced and the plain rows a_ij / b_j.  p_prev is then dead once the rows are open.  STRICT builds
+  // keep the reference's p_prev + (sum a_ij k_j) * t_step.
+  template <bool FULL>
+  __device__ __forceinline__ double row_coef(int r, int j) const {
+    if (PRESCALED && FULL) return r < S ? A.ha[r * DFB_MAX_STAGES + j] : A.hb[j];
+    return r < S ? A.a[r * DFB_MAX_STAGES + j] : A.b[j];
+  }
+  __device__ __forceinline__ static constexpr bool row_has(int r, int j) {
+    return r < S ? (AMASK & amask_bit(r, j)) != 0ull : (BMASK & (1u << j)) != 0u;
+  }
+  template <bool FULL>
+  __device__ __forceinline__ double row_open(int r, int u, int n, int m_stored) {
+    // running sum of row r (r < S: stage row, r == S: the b row) over k[0 .. m_stored-1]
+    double acc = PRESCALED ? p_prev[u][n] : 0.0;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      if (j >= m_stored) break;
+      if (!row_has(r, j)) continue;
+      if (PRESCALED) acc = fma(k[u][j][n], row_coef<FULL>(r, j), acc);
+      else acc = acc + k[u][j][n] * row_coef<FULL>(r, j);
+    }
+    return acc;
+  }
+
+  template <bool FULL>
+  __device__ __forceinline__ void step_fold(double t_step) {
+    constexpr int M = (S + 1) / 2;
+    constexpr bool SCALE = PRESCALED && !FULL;
+    double row[TPT][S + 1][N];  // rows M+1 .. S only (the rest is never touched and takes no registers)
+    double kj[TPT][N];
+    t_prev = t_curr;
+#pragma unroll
+    for (int u = 0; u < TPT; ++u)
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        k[u][0][n] = SCALE ? d_curr[u][n] * t_step : d_curr[u][n];
+        p_prev[u][n] = p_curr[u][n];
+      }
+#pragma unroll
+    for (int i = 1; i < S; ++i) {
+      t_curr = t_prev + (FULL ? A.hc[i] : A.c[i] * t_step);
+#pragma unroll
+      for (int u = 0; u < TPT; ++u)
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+          const double acc = i <= M ? row_open<FULL>(i, u, n, i) : row[u][i][n];
+          p_curr[u][n] = PRESCALED ? acc : p_prev[u][n] + acc * t_step;
+          if (i == M) {
+#pragma unroll
+            for (int r = M + 1; r <= S; ++r) row[u][r][n] = row_open<FULL>(r, u, n, M);
+          }
+        }
+      if (i < M) {
+        rhs_stage(i);
+        if (SCALE) {
+#pragma unroll
+          for (int u = 0; u < TPT; ++u)
+#pragma unroll
+            for (int n = 0; n < N; ++n) k[u][i][n] *= t_step;
+        }
+      } else {
+        rhs_all(kj);
+#pragma unroll
+        for (int u = 0; u < TPT; ++u)
+#pragma unroll
+          for (int n = 0; n < N; ++n) {
+            const double kv = SCALE ? kj[u][n] * t_step : kj[u][n];
+#pragma unroll
+            for (int r = i + 1; r <= S; ++r) {
+              if (!row_has(r, i)) continue;
+              if (PRESCALED) row[u][r][n] = fma(kv, row_coef<FULL>(r, i), row[u][r][n]);
+              else row[u][r][n] = row[u][r][n] + kv * row_coef<FULL>(r, i);
+            }
+          }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < TPT; ++u)
+#pragma unroll
+      for (int n = 0; n < N; ++n)
+        p_curr[u][n] = PRESCALED ? row[u][S][n] : p_prev[u][n] + row[u][S][n] * t_step;
+    t_curr = t_prev + t_step;
+    rhs_all(d_curr);
+  }
+
   template <bool FULL>
   __device__ __forceinline__ void step(double t_step) {
+    if constexpr (FOLD) {
+      step_fold<FULL>(t_step);
+      return;
+    }
     // k[0] = d_curr (state.rs:95-96); the caller guarantees d_curr is current
     t_prev = t_curr;
 #pragma unroll
@@ -329,6 +434,8 @@ struct OdeFixedPeriodicStepper : OdeFixedStepper<Sys, S, AMASK, BMASK, PRESCALED
 #pragma unroll
     for (int l = 0; l < DFB_MAX_LOCATORS; ++l) last_call[l] = 0.0;
     const double h = A.h;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double t_quiet = -inf;
 
 #pragma unroll 1
     while (t_curr < A.t1) {
@@ -342,42 +449,52 @@ struct OdeFixedPeriodicStepper : OdeFixedStepper<Sys, S, AMASK, BMASK, PRESCALED
         ++n_rhs;
       }
       const double h_req = fmin(h, A.t1 - t_curr);  // solver.rs:293
-      if (h_req == h) this->template step<true>(h);
-      else this->template step<false>(h_req);
-      n_rhs += S;
+      const double t_next = t_curr + h_req;         // = t_curr after make_step(h_req) (state.rs:117)
 
-      // HListLocateEarliest over Periodic locators (loc.rs:318-334, 821-835, 1002-1011)
+      // HListLocateEarliest over Periodic locators (loc.rs:318-334, 821-835, 1002-1011).  Detection
+      // and location read the time grid only, so they run BEFORE the step on (t_curr, t_next): when an
+      // event is found the reference's full step would be undone (solver.rs:300) and is not taken at
+      // all — its S + 1 right-hand-side calls are counted, nothing else of it survives (d_curr is
+      // re-evaluated from the same state to the same bits).  `t_quiet` is a lower bound of the next
+      // period boundary of any locator, a wide margin (1e-9 relative, ~10^7 ulp) below it: while t_next
+      // stays under it floor((t - o) / T) cannot have moved, and the two FP64 divisions per locator
+      // and step are skipped; the exact test decides inside the margin.
       bool found = false;
       double best_t = 0.0;
       int best_l = 0;
+      if (!(t_next < t_quiet)) {
+        double quiet = inf;
 #pragma unroll
-      for (int l = 0; l < DFB_MAX_LOCATORS; ++l) {
-        if (l >= A.n_loc) break;
-        const dfb_locator& L = A.loc[l];
-        if (L.dedup && ((has_last_call >> l) & 1u) && !(t_prev > last_call[l])) continue;
-        const double fl_prev = floor((t_prev - L.offset) / L.period);
-        const double fl_curr = floor((t_curr - L.offset) / L.period);
-        if (fl_prev < fl_curr) {
-          const double tl = fl_curr * L.period + L.offset;
-          if (!found || tl < best_t) {
-            found = true;
-            best_t = tl;
-            best_l = l;
+        for (int l = 0; l < DFB_MAX_LOCATORS; ++l) {
+          if (l >= A.n_loc) break;
+          const dfb_locator& L = A.loc[l];
+          const double fl_prev = floor((t_curr - L.offset) / L.period);
+          const double fl_curr = floor((t_next - L.offset) / L.period);
+          const double bound = (fl_curr + 1.0) * L.period + L.offset;
+          const double q = bound - 1e-9 * (fabs(bound) + fabs(L.offset) + fabs(L.period));
+          quiet = (L.period > 0.0 && q < quiet) ? q : ((L.period > 0.0) ? quiet : -inf);
+          if (L.dedup && ((has_last_call >> l) & 1u) && !(t_curr > last_call[l])) continue;
+          if (fl_prev < fl_curr) {
+            const double tl = fl_curr * L.period + L.offset;
+            if (!found || tl < best_t) {
+              found = true;
+              best_t = tl;
+              best_l = l;
+            }
           }
         }
+        t_quiet = quiet;
       }
-      if (found && best_t >= t_prev) {  // solver.rs:299-307
-        // undo_step (state.rs:146-150); k[0] still holds d_prev
-        t_curr = t_prev;
+      if (found && best_t >= t_curr) {  // solver.rs:299-307
+        n_rhs += S + 1;  // the undone full step and the k[0] make_step re-evaluates after undo_step
+        if (!Sys::pure_rhs) {  // that re-evaluation sees t_prev == t_curr, p_prev == p_curr (state.rs:146-150)
+          t_prev = t_curr;
 #pragma unroll
-        for (int u = 0; u < TPT; ++u)
+          for (int u = 0; u < TPT; ++u)
 #pragma unroll
-          for (int n = 0; n < N; ++n) {
-            p_curr[u][n] = p_prev[u][n];
-            d_curr[u][n] = k[u][0][n];
-          }
-        this->rhs_all(d_curr);  // t_prev == t_curr: make_step evaluates k[0] again
-        ++n_rhs;
+            for (int n = 0; n < N; ++n) p_prev[u][n] = p_curr[u][n];
+          this->rhs_all(d_curr);
+        }
         this->template step<false>(best_t - t_curr);
         n_rhs += S;
         // commit_step; make_zero_step (state.rs:141-144)
@@ -418,6 +535,9 @@ struct OdeFixedPeriodicStepper : OdeFixedStepper<Sys, S, AMASK, BMASK, PRESCALED
           }
         }
       } else {
+        if (h_req == h) this->template step<true>(h);
+        else this->template step<false>(h_req);
+        n_rhs += S;
         ++n_steps;
       }
     }

@@ -131,9 +131,13 @@ bool try_launch_periodic(int S_rt, unsigned long long amask, unsigned bmask, con
   if constexpr (Sys::N >= 8) {
     const char* e = getenv("DFB_PERIODIC_MINB");
     const int m = e ? atoi(e) : 5;
-    wide = m == 3 || m == 5 || m == 6;
+    wide = m == 3 || m == 4 || m == 5 || m == 6 || m == 7;
     const auto g128 = pick(128), g64 = pick(64);
-    if (m == 3)
+    if (m == 4)
+      ode_fixed_periodic_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 1, 4><<<unsigned(g128.grid), g128.block, 0, stream>>>(A);
+    else if (m == 7)
+      ode_fixed_periodic_kernel<Sys, S, AMASK, BMASK, kPrescaled, 64, 1, 7><<<unsigned(g64.grid), g64.block, 0, stream>>>(A);
+    else if (m == 3)
       ode_fixed_periodic_kernel<Sys, S, AMASK, BMASK, kPrescaled, kBlock, 1, 3><<<unsigned(g128.grid), g128.block, 0, stream>>>(A);
     else if (m == 5)
       ode_fixed_periodic_kernel<Sys, S, AMASK, BMASK, kPrescaled, 64, 1, 5><<<unsigned(g64.grid), g64.block, 0, stream>>>(A);

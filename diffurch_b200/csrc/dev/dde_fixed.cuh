@@ -73,6 +73,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16_saddr(unsigned smem_addr, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int PENDING>
 __device__ __forceinline__ void cp_async_wait() {
@@ -285,6 +288,14 @@ struct DdeFixedStepper {
     for (int q = 0; q < F / 2; ++q) cp_async16(d + 2 * (lane + 32 * q), g + 2 * (lane + 32 * q));
     if ((F & 1) && lane < 16) cp_async16(d + 2 * (lane + 32 * (F / 2)), g + 2 * (lane + 32 * (F / 2)));
   }
+  // issue_fetch with the lane's shared-memory address and ring column computed once (lean steady loop)
+  __device__ __forceinline__ void issue_fetch_lean(int rec, unsigned sm_lane, const double* ring_lane) {
+    const double* g = ring_lane + (unsigned(rec) & unsigned(A.ring_capacity - 1)) * slot_stride;
+    const unsigned d = sm_lane + (unsigned(rec) & unsigned(kDdeSmemSlots - 1)) * unsigned(kWarpRec * sizeof(double));
+#pragma unroll
+    for (int q = 0; q < F / 2; ++q) cp_async16_saddr(d + 512u * q, g + 64 * q);
+    if ((F & 1) && lane < 16) cp_async16_saddr(d + 512u * (F / 2), g + 64 * (F / 2));
+  }
   // per-lane copy of one record (lanes of the warp disagree on the window position)
   __device__ __forceinline__ void copy_own_column(int rec) {
     const double* g = warp_block(rec) + lane;
@@ -481,6 +492,45 @@ struct DdeFixedStepper {
         refill(s, tau, h);
         ++s;
         on_step(unsigned(s));
+      }
+      // Phase B, lean form: while the step AFTER the one being taken is a counted full step as well, the
+      // delay is warp-uniform, no prune replay and no trace are asked for, the per-step bookkeeping of
+      // refill_steady() (same window rule, same invariants) shrinks to: two additions for the earliest
+      // lookup time of the next step, one predicated slide, one record fetch, the async-group wait.  A
+      // shard of the ensemble (1-2 warps per SM sub-partition) spent half of its time in the branches
+      // and dependent selects of the general form (profiles/r2_dde_small_shard_lean_loop.txt).
+      if (counted && uniform && !track_oldest && loaded && A.trace_every <= 0) {
+        const unsigned sm_lane = (unsigned)__cvta_generic_to_shared(sm) + 16u * unsigned(lane);
+        const double* ring_lane = A.ring + warp_base + 2 * lane;
+#pragma unroll 1
+        while (s + 1 < n_full && w + 4 < s) {
+          {
+            step<true, true>(h);
+            commit<true>(s, h);
+            const double tt_min = (t_curr + A.hc_min) - tau;
+            const int w_was = w;
+            if (tw1 <= tt_min) {
+              ++w;
+              tw0 = tw1;
+              tw1 = tw1 + h;
+            }
+            if (tw1 <= tt_min) {  // more than one record per step: rounding of the grid, rare
+              do {
+                ++w;
+                tw0 = tw1;
+                tw1 = tw1 + h;
+              } while (tw1 <= tt_min);
+              for (int r = w_was + 3; r < w + 2; ++r) issue_fetch_lean(r, sm_lane, ring_lane);
+            }
+            if (w != w_was) issue_fetch_lean(w + 2, sm_lane, ring_lane);  // w + 2 < s - 2: committed long ago
+            cp_async_commit();
+            cp_async_wait<1>();  // record w + 1 was issued one step ago at the latest
+            __syncwarp();
+            p0 = smem_block(w) + lane;
+            p1 = smem_block(w + 1) + lane;
+            ++s;
+          }
+        }
       }
       // Phase B (steady): full steps whose lookups all lie after t_init and before the
       // last committed time.  What the reference checks on every lookup is checked once

@@ -176,6 +176,20 @@ struct DdeFixedStepperT {
     }
   }
 
+  // issue_fetch with the lane's shared-memory address and ring columns computed once (lean steady loop)
+  __device__ __forceinline__ void issue_fetch_lean(int rec, unsigned sm_lane, const double* const* ring_lane) {
+    const unsigned slot_off = (unsigned(rec) & unsigned(A.ring_capacity - 1)) * slot_stride;
+    const unsigned d0 = sm_lane + (unsigned(rec) & unsigned(kDdeSmemSlots - 1)) * unsigned(TPT * kWarpRec * sizeof(double));
+#pragma unroll
+    for (int u = 0; u < TPT; ++u) {
+      const double* g = ring_lane[u] + slot_off;
+      const unsigned d = d0 + unsigned(u * kWarpRec * sizeof(double));
+#pragma unroll
+      for (int q = 0; q < F / 2; ++q) cp_async16_saddr(d + 512u * q, g + 64 * q);
+      if ((F & 1) && lane < 16) cp_async16_saddr(d + 512u * (F / 2), g + 64 * (F / 2));
+    }
+  }
+
   // commit_step (state.rs:122-139): pre-combined interpolant of the step just taken -> ring
   template <bool FULL>
   __device__ __forceinline__ void commit(int s, double t_step) {
@@ -316,6 +330,40 @@ struct DdeFixedStepperT {
         refill(s, tau, h);
         ++s;
         on_step(unsigned(s));
+      }
+      // Phase B, lean form (see DdeFixedStepper::run): counted full steps, no prune replay, no trace
+      if (counted && !track_oldest && loaded && A.trace_every <= 0) {
+        const unsigned sm_lane = (unsigned)__cvta_generic_to_shared(sm) + 16u * unsigned(lane);
+        const double* ring_lane[TPT];
+#pragma unroll
+        for (int u = 0; u < TPT; ++u) ring_lane[u] = A.ring + warp_base[u] + 2 * lane;
+#pragma unroll 1
+        while (s + 1 < n_full && w + 4 < s) {
+          step<true, true>(h);
+          commit<true>(s, h);
+          const double tt_min = (t_curr + A.hc_min) - tau;
+          const int w_was = w;
+          if (tw1 <= tt_min) {
+            ++w;
+            tw0 = tw1;
+            tw1 = tw1 + h;
+          }
+          if (tw1 <= tt_min) {  // more than one record per step: rounding of the grid, rare
+            do {
+              ++w;
+              tw0 = tw1;
+              tw1 = tw1 + h;
+            } while (tw1 <= tt_min);
+            for (int r = w_was + 3; r < w + 2; ++r) issue_fetch_lean(r, sm_lane, ring_lane);
+          }
+          if (w != w_was) issue_fetch_lean(w + 2, sm_lane, ring_lane);
+          cp_async_commit();
+          cp_async_wait<1>();
+          __syncwarp();
+          p0 = smem_block(w) + lane;
+          p1 = smem_block(w + 1) + lane;
+          ++s;
+        }
       }
       // Phase B (steady)
 #pragma unroll 1

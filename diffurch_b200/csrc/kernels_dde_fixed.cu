@@ -59,11 +59,26 @@ bool try_launch(int S_rt, int I_rt, unsigned long long am, unsigned bm, unsigned
                          int((kBlock / 32) * kDdeSmemSlots * Stepper::kWarpRec * sizeof(double)));
   }
   const size_t warps = (A.n_traj + 31) / 32;
-  // two members per thread pay once ~20 warps per SM exist (measured: 2^16 members 5.18 ms one per
-  // thread vs 5.34 two per thread; 2^17 members 9.45 vs 9.32)
-  int tpt = warps >= size_t(n_sm) * 20 ? 2 : 1;
   // below ~16 warps per SM one warp per block spreads the ensemble over every SM sub-partition
   int block = warps >= size_t(n_sm) * 16 ? kBlock : (warps >= size_t(n_sm) * 8 ? 64 : 32);
+  // One or two members per thread: both builds keep 16 warps per SM resident, so a launch is
+  // floor(waves) full waves at the HBM-bound rate plus a tail that cannot finish faster than a lone warp
+  // runs its own dependent instruction stream (measured: ~0.48 of a full wave's time with one member per
+  // thread, ~0.33 with two).  The cheaper prediction wins; two members per thread carry a 3 % handicap
+  // (measured at equal predictions).  2^18 members: one per thread 17.9 ms vs 18.3; 3/8 of it: two per
+  // thread 6.6 vs 7.5 ms; 1/8: one per thread 2.55 vs 3.4 ms (profiles/r2_dde_geometry_model.txt).
+  auto predicted = [&](int members_per_thread) {
+    const double slots = double(n_sm) * 16.0;  // resident warps on the device
+    const double waves = double((A.n_traj + 32 * members_per_thread - 1) / (32 * members_per_thread)) / slots;
+    const double t_full = slots * 32.0 * members_per_thread;
+    const double t_min = (members_per_thread == 1 ? 0.48 : 0.33) * t_full;
+    const double whole = double(size_t(waves));
+    const double frac = waves - whole;
+    double t = whole * t_full;
+    if (frac > 0.0) t += (frac * t_full > t_min) ? frac * t_full : t_min;
+    return members_per_thread == 1 ? t : 1.03 * t;
+  };
+  int tpt = predicted(2) < predicted(1) ? 2 : 1;
   if (const char* e = getenv("DFB_DDE_TPT")) tpt = atoi(e) == 2 ? 2 : 1;
   if (const char* e = getenv("DFB_DDE_BLOCK")) block = atoi(e) == 32 ? 32 : (atoi(e) == 64 ? 64 : kBlock);
   if (tpt == 2) {

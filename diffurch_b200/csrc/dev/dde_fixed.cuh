@@ -82,6 +82,9 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
 }
 
+#ifndef DFB_DDE_AHEAD
+#define DFB_DDE_AHEAD 3  // 2 .. 5 (8 staging slots in the PRE build)
+#endif
 constexpr int kDdeSmemSlots = 4;  // records w .. w+2 of the window plus one being overwritten
 
 // Horner evaluation of one staged record; p = this lane's column of the record block
@@ -167,13 +170,17 @@ struct DdeFixedStepper {
   static constexpr int NP = Sys::NP > 0 ? Sys::NP : 1;
   static constexpr int F = N * I;          // doubles per record
   static constexpr int kWarpRec = F * 32;  // doubles of one warp's record block (F x 256 bytes)
+  // staging slots: records w .. w+2 plus one being overwritten; the PRE build (lone warps: a shard of the
+  // ensemble) prefetches one record deeper (w+3) so that a step never waits on HBM latency
+  static constexpr int kSlots = PRE ? 8 : kDdeSmemSlots;
+  static constexpr int kAhead = PRE ? DFB_DDE_AHEAD : 2;  // the lean loop fetches record w + kAhead
 
   const DdeFixedArgs& A;
   size_t gid;
   size_t g_thread;  // global thread index (= trajectory index for valid lanes)
   bool valid;
   int lane;
-  double* sm;  // this warp's staging area [kDdeSmemSlots][F][32]
+  double* sm;  // this warp's staging area [kSlots][F][32]
   double t_curr, t_prev;
   double p_curr[N], p_prev[N], d_curr[N];
   double k[S][N];
@@ -279,7 +286,7 @@ struct DdeFixedStepper {
     return A.ring + (slot * slot_stride + warp_base);
   }
   __device__ __forceinline__ double* smem_block(int rec) const {
-    return sm + (unsigned(rec) & unsigned(kDdeSmemSlots - 1)) * unsigned(kWarpRec);
+    return sm + (unsigned(rec) & unsigned(kSlots - 1)) * unsigned(kWarpRec);
   }
   __device__ __forceinline__ void issue_fetch(int rec) {
     const double* g = warp_block(rec);
@@ -291,7 +298,7 @@ struct DdeFixedStepper {
   // issue_fetch with the lane's shared-memory address and ring column computed once (lean steady loop)
   __device__ __forceinline__ void issue_fetch_lean(int rec, unsigned sm_lane, const double* ring_lane) {
     const double* g = ring_lane + (unsigned(rec) & unsigned(A.ring_capacity - 1)) * slot_stride;
-    const unsigned d = sm_lane + (unsigned(rec) & unsigned(kDdeSmemSlots - 1)) * unsigned(kWarpRec * sizeof(double));
+    const unsigned d = sm_lane + (unsigned(rec) & unsigned(kSlots - 1)) * unsigned(kWarpRec * sizeof(double));
 #pragma unroll
     for (int q = 0; q < F / 2; ++q) cp_async16_saddr(d + 512u * q, g + 64 * q);
     if ((F & 1) && lane < 16) cp_async16_saddr(d + 512u * (F / 2), g + 64 * (F / 2));
@@ -410,10 +417,12 @@ struct DdeFixedStepper {
       tw0 = tw1;
       tw1 = tw1 + h;
     }
+    const bool jumped = w + 2 > r;  // moved by more than one record (rounding of the grid, rare)
 #pragma unroll 1
     for (; r <= w + 2 && r <= s; ++r) issue_fetch(r);
     cp_async_commit();
-    cp_async_wait<1>();  // record w + 1 was issued one refill ago at the latest
+    if (jumped) cp_async_wait<0>();  // its records may have been issued only now
+    else cp_async_wait<1>();  // record w + 1 was issued one refill ago at the latest
     __syncwarp();
     p0 = smem_block(w) + lane;
     p1 = smem_block(w + 1) + lane;
@@ -502,34 +511,39 @@ struct DdeFixedStepper {
       if (counted && uniform && !track_oldest && loaded && A.trace_every <= 0) {
         const unsigned sm_lane = (unsigned)__cvta_generic_to_shared(sm) + 16u * unsigned(lane);
         const double* ring_lane = A.ring + warp_base + 2 * lane;
+        // records <= w + 2 are issued (invariant of refill); the deeper prefetch starts with the ones up to w + kAhead
+        if (s + 1 < n_full && w + kAhead + 2 < s) {
+          for (int r = w + 3; r <= w + kAhead; ++r) issue_fetch_lean(r, sm_lane, ring_lane);
+          cp_async_commit();
+        }
 #pragma unroll 1
-        while (s + 1 < n_full && w + 4 < s) {
-          {
-            step<true, true>(h);
-            commit<true>(s, h);
-            const double tt_min = (t_curr + A.hc_min) - tau;
-            const int w_was = w;
-            if (tw1 <= tt_min) {
+        while (s + 1 < n_full && w + kAhead + 2 < s) {
+          step<true, true>(h);
+          commit<true>(s, h);
+          const double tt_min = (t_curr + A.hc_min) - tau;
+          const int w_was = w;
+          if (tw1 <= tt_min) {
+            ++w;
+            tw0 = tw1;
+            tw1 = tw1 + h;
+          }
+          if (tw1 <= tt_min) {  // more than one record per step: rounding of the grid, rare
+            do {
               ++w;
               tw0 = tw1;
               tw1 = tw1 + h;
-            }
-            if (tw1 <= tt_min) {  // more than one record per step: rounding of the grid, rare
-              do {
-                ++w;
-                tw0 = tw1;
-                tw1 = tw1 + h;
-              } while (tw1 <= tt_min);
-              for (int r = w_was + 3; r < w + 2; ++r) issue_fetch_lean(r, sm_lane, ring_lane);
-            }
-            if (w != w_was) issue_fetch_lean(w + 2, sm_lane, ring_lane);  // w + 2 < s - 2: committed long ago
+            } while (tw1 <= tt_min);
+            for (int r = w_was + kAhead + 1; r < w + kAhead; ++r) issue_fetch_lean(r, sm_lane, ring_lane);
             cp_async_commit();
-            cp_async_wait<1>();  // record w + 1 was issued one step ago at the latest
-            __syncwarp();
-            p0 = smem_block(w) + lane;
-            p1 = smem_block(w + 1) + lane;
-            ++s;
+            cp_async_wait<0>();  // the window jumped: its records may have been issued only now
           }
+          if (w != w_was) issue_fetch_lean(w + kAhead, sm_lane, ring_lane);  // committed long ago (w + kAhead + 2 < s)
+          cp_async_commit();
+          cp_async_wait<kAhead - 1>();  // record w + 1 was issued kAhead - 1 steps ago at the latest
+          __syncwarp();
+          p0 = smem_block(w) + lane;
+          p1 = smem_block(w + 1) + lane;
+          ++s;
         }
       }
       // Phase B (steady): full steps whose lookups all lie after t_init and before the
@@ -577,7 +591,7 @@ template <class Sys, int S, int I, unsigned long long AMASK, unsigned BMASK, uns
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
     dde_fixed_kernel(const __grid_constant__ DdeFixedArgs A) {
   using Stepper = DdeFixedStepper<Sys, S, I, AMASK, BMASK, BIMASK, PRE>;
-  // (blockDim.x / 32) * kDdeSmemSlots * kWarpRec doubles, sized by the launcher: BLOCK is the launch
+  // (blockDim.x / 32) * Stepper::kSlots * kWarpRec doubles, sized by the launcher: BLOCK is the launch
   // bound, the block itself is chosen from the ensemble size (host/launch_geometry.hpp)
   extern __shared__ __align__(16) double smem[];
   const size_t g = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -586,7 +600,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
   if ((g & ~size_t(31)) >= A.n_traj) return;  // whole warp past the end (warp-uniform exit)
   const bool valid = g < A.n_traj;
   const size_t gid = valid ? g : A.n_traj - 1;
-  Stepper st(A, g, gid, valid, smem + (threadIdx.x / 32) * kDdeSmemSlots * Stepper::kWarpRec);
+  Stepper st(A, g, gid, valid, smem + (threadIdx.x / 32) * Stepper::kSlots * Stepper::kWarpRec);
   st.run();
 }
 

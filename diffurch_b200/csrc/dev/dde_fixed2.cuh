@@ -273,10 +273,12 @@ struct DdeFixedStepperT {
       tw0 = tw1;
       tw1 = tw1 + h;
     }
+    const bool jumped = w + 2 > r;  // moved by more than one record (rounding of the grid, rare)
 #pragma unroll 1
     for (; r <= w + 2 && r <= s; ++r) issue_fetch(r);
     cp_async_commit();
-    cp_async_wait<1>();
+    if (jumped) cp_async_wait<0>();  // its records may have been issued only now
+    else cp_async_wait<1>();
     __syncwarp();
     p0 = smem_block(w) + lane;
     p1 = smem_block(w + 1) + lane;
@@ -355,8 +357,12 @@ struct DdeFixedStepperT {
               tw1 = tw1 + h;
             } while (tw1 <= tt_min);
             for (int r = w_was + 3; r < w + 2; ++r) issue_fetch_lean(r, sm_lane, ring_lane);
+            issue_fetch_lean(w + 2, sm_lane, ring_lane);
+            cp_async_commit();
+            cp_async_wait<0>();  // the window jumped: its records may have been issued only now
+          } else if (w != w_was) {
+            issue_fetch_lean(w + 2, sm_lane, ring_lane);
           }
-          if (w != w_was) issue_fetch_lean(w + 2, sm_lane, ring_lane);
           cp_async_commit();
           cp_async_wait<1>();
           __syncwarp();

@@ -87,7 +87,7 @@ bool try_launch(int S_rt, int I_rt, unsigned long long am, unsigned bm, unsigned
     kernel2<<<unsigned(grid), block, smem, stream>>>(A);
   } else {
     const size_t grid = (A.n_traj + block - 1) / block;
-    const size_t smem = size_t(block / 32) * kDdeSmemSlots * Stepper::kWarpRec * sizeof(double);
+    size_t smem = size_t(block / 32) * kDdeSmemSlots * Stepper::kWarpRec * sizeof(double);
     // Few warps per SM (a shard of the ensemble): nothing hides the latency of a warp's own instruction
     // stream, so the build WITHOUT the 72-register cap runs — the scheduler may then hoist the step's
     // state-independent history evaluations above the dependent stage chain.  DFB_DDE_RELAXED=0|1 overrides.
@@ -96,11 +96,13 @@ bool try_launch(int S_rt, int I_rt, unsigned long long am, unsigned bm, unsigned
     if (const char* e = getenv("DFB_DDE_RELAXED")) relaxed = atoi(e) != 0;
     if (relaxed) {
       auto kernel1r = dde_fixed_kernel<Sys, S, I, AMASK, BMASK, BIMASK, kBlock, 2, true>;
+      using StepperPre = DdeFixedStepper<Sys, S, I, AMASK, BMASK, BIMASK, true>;
+      smem = size_t(block / 32) * StepperPre::kSlots * Stepper::kWarpRec * sizeof(double);
       static bool once = false;
       if (!once) {
         cudaFuncSetAttribute(kernel1r, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(kernel1r, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             int((kBlock / 32) * kDdeSmemSlots * Stepper::kWarpRec * sizeof(double)));
+                             int((kBlock / 32) * StepperPre::kSlots * Stepper::kWarpRec * sizeof(double)));
         once = true;
       }
       kernel1r<<<unsigned(grid), block, smem, stream>>>(A);

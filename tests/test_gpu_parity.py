@@ -471,6 +471,34 @@ def test_dde_hot_path_delay_is_an_exact_multiple_of_the_step(oracle):
             assert np.max(np.abs(f.p - o.p)) < 1e-11, (system.name, tau, h)
 
 
+def test_dde_hot_path_builds_agree_lean_loop(oracle):
+    # The three builds of the constant-delay hot path — one member per thread without the register cap (PRE:
+    # pre-evaluated delayed values, lean steady loop, record w+3 prefetched into 8 staging slots), one member
+    # per thread capped at 72 registers, two members per thread — run the same arithmetic per member: identical
+    # bits among themselves, the oracle's step grid, the FAST tolerance against the oracle's state.  Delays from
+    # 6 to 200 steps put the window anywhere from right behind the write head to the far end of the ring.
+    k = 0.5 + np.arange(133) / 132.0                       # ragged: 4 warps + 5 members
+    for tau, h, t1 in ((1.0, 0.02, 25.0), (0.3, 0.05, 30.0), (2.0, 0.01, 12.0), (1.0, 0.037, 20.0)):
+        mk = lambda arith: (d.Solver.new().max_delay(tau).initial(d.InitFn(d.SIN)).interval(0.0, t1).stepsize(h)
+                            .equation(d.systems.DdeLinear, cases.dde_params(k, tau)).arith(arith))
+        o = oracle.run_solver(mk("strict"), n_threads=8)
+        runs = {}
+        for name, env in (("pre", {"DFB_DDE_TPT": "1"}), ("capped", {"DFB_DDE_TPT": "1", "DFB_DDE_RELAXED": "0"}),
+                          ("two", {"DFB_DDE_TPT": "2"})):
+            os.environ.update(env)
+            try:
+                g = mk("fast").run()
+            finally:
+                for e in env:
+                    del os.environ[e]
+            assert g.totals["kernel_kind"] == d.abi.KERNEL_DDE_FIXED and np.all(g.status == 0), name
+            assert np.array_equal(g.steps, o.steps) and np.array_equal(g.t, o.t), name
+            assert np.max(np.abs(g.p - o.p)) < 1e-10, (name, tau, h)
+            runs[name] = g
+        assert np.array_equal(runs["pre"].p, runs["capped"].p), (tau, h)
+        assert np.array_equal(runs["pre"].p, runs["two"].p), (tau, h)
+
+
 def test_dde_hot_path_trace_policy(oracle):
     # Trace (every k-th on_step call, capacity-bounded) inside both DDE hot kernels: the time grid and
     # the sample counts are the oracle's bit for bit, the samples within the FAST tolerance, the last
@@ -1014,6 +1042,32 @@ def test_periodic_kernel_two_locators_and_event_log(oracle):
     gen = run_general(mk)
     assert np.array_equal(hot.p, gen.p) and np.array_equal(hot.aux, gen.aux)
     assert np.array_equal(hot.event_t[:, :ne], gen.event_t[:, :ne])
+
+
+@pytest.mark.parametrize("h,period,offset,t1", [
+    (0.25, 0.5, 0.0, 60.0),      # boundaries exactly on grid points (all values dyadic)
+    (0.01, 0.1, 0.0, 40.0),      # inexact period and step: floor((t - o) / T) sits within an ulp of an integer
+    (0.037, 0.5, 0.123, 500.0),  # incommensurate, long horizon (the quiet-interval margin grows with t)
+    (0.3, 0.1, 0.05, 12.0),      # several periods per step: every step has an event
+])
+def test_periodic_kernel_quiet_interval_same_events_as_oracle(oracle, h, period, offset, t1):
+    # the kernel skips the floor((t - o) / T) test while t_next is provably below the next period boundary
+    # (dev/ode_fixed.cuh, `t_quiet`) and predicts events instead of stepping and undoing: event times, indices
+    # and every counter must still be the reference's (loc.rs:318-334, solver.rs:299-308), bit for bit
+    lam = np.array([-0.01, 0.003, 0.0]).reshape(-1, 1)
+
+    def mk():
+        return (d.Solver.new().initial(np.ones((3, 1))).interval(0.0, t1).stepsize(h)
+                .equation(d.systems.Linear1, lam).on_mut(d.Periodic(period, offset), "renormalize")
+                .log_events(d.EventLog(2048)))
+    hot = mk().run()
+    assert hot.totals["kernel_kind"] == KERNEL_ODE_FIXED_PERIODIC
+    o = oracle.run_solver(mk(), n_threads=2)
+    assert_same_counters(hot, o)
+    assert np.array_equal(hot.event_n, o.event_n) and int(hot.event_n[0]) > 10
+    ne = min(int(hot.event_n[0]), 2048)
+    assert np.array_equal(hot.event_t[:, :ne], o.event_t[:, :ne])
+    assert np.array_equal(hot.p, o.p) and np.array_equal(hot.t, o.t)
 
 
 def test_periodic_kernel_stop_integration_is_per_lane(oracle):

@@ -465,9 +465,11 @@ def other_config_legs(d, peak_tflops):
         # configs[1], adaptive half: 307 flop per ATTEMPTED step (252 + error estimate + controller)
         "lorenz_2^20_adaptive_rktp64_tol1e-9": (lambda: cases.lorenz(n=1 << 20, t1=T_END, arith="fast").stepsize(auto), 307.0, 0.0),
         # configs[3]: §8d step formula with N = 2 (F_rhs = 1) / N = 4 (F_rhs = 0); a bisection iteration is
-        # N x 4 FMA (Horner, I = 5) + detector (1 / 6 flop) + 3 (midpoint, width)
-        "bouncing_ball_2^19_t=[0,8]": (lambda: cases.bouncing_ball(n=1 << 19, t1=8.0, arith="fast", events=0), step_flops(2, 1), 2 * 8 + 1 + 3.0),
-        "egg_billiard_2^19_200_reflections": (lambda: cases.egg_billiard(n=1 << 19, reflections=200, arith="fast", events=0), step_flops(4, 0), 4 * 8 + 6 + 3.0),
+        # 4 FMA (Horner, I = 5) per component the detector reads + detector (1 / 6 flop) + 3 (midpoint, width):
+        # the ball's detectors read one component each (the kernel folds the other one away since the locators
+        # are compile-time constants), the egg's boundary function reads x and y of its N = 4
+        "bouncing_ball_2^19_t=[0,8]": (lambda: cases.bouncing_ball(n=1 << 19, t1=8.0, arith="fast", events=0), step_flops(2, 1), 1 * 8 + 1 + 3.0),
+        "egg_billiard_2^19_200_reflections": (lambda: cases.egg_billiard(n=1 << 19, reflections=200, arith="fast", events=0), step_flops(4, 0), 2 * 8 + 6 + 3.0),
         # configs[4]: Lorenz + 3x3 variational block (N = 12), QR every 0.5; flop/step by the same
         # formula as the headline: 12(2*21+6) + 12*13 + 13 + 7*F_rhs.  F_rhs = 8 + 33 + 1 = 42: the Jacobian
         # product WITHOUT its structural zero / unit entries (11 flop per column) — what the FAST kernel

@@ -44,9 +44,22 @@ namespace DFB_NS {
 // filter, boolean-detection and other-location branches from the per-step detection code (which
 // is ~45 % of the instructions of the bouncing-ball run in the generic profile).
 // LEAN = no Trace policy on this problem (known at launch): the per-step `on_step` test disappears.
+// SPEC != kEvSpecRuntime (SIMPLE only): the locators themselves are known at compile time — one byte per
+// locator: detector id (bits 0-3), detection (bits 4-5: DFB_DET_ZERO / ABOVE_ZERO / BELOW_ZERO), DedupLocF
+// (bit 6) — and n_loc == NLOC.  The detector switch of the system folds to the one function asked for (the
+// bisection of the bouncing ball then interpolates x only, not x and v), and the per-step detection carries
+// no descriptor loads, no selects on the detection kind and no tests of n_loc / dedup.
+constexpr unsigned kEvSpecRuntime = 0xFFFFFFFFu;
+__host__ __device__ constexpr unsigned ev_spec_byte(int detector_id, int detection, bool dedup) {
+  return unsigned(detector_id & 15) | (unsigned(detection & 3) << 4) | (dedup ? 64u : 0u);
+}
 template <class Sys, int S_, int I_, unsigned long long AMASK, unsigned BMASK, bool FAST, int NLOC, bool SIMPLE = false,
-          bool LEAN = false>
+          bool LEAN = false, unsigned SPEC = kEvSpecRuntime>
 struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
+  static constexpr bool HAS_SPEC = SIMPLE && SPEC != kEvSpecRuntime;
+  __device__ __forceinline__ static constexpr int spec_id(int l) { return int((SPEC >> (8 * l)) & 15u); }
+  __device__ __forceinline__ static constexpr int spec_detection(int l) { return int((SPEC >> (8 * l + 4)) & 3u); }
+  __device__ __forceinline__ static constexpr bool spec_dedup(int l) { return ((SPEC >> (8 * l + 6)) & 1u) != 0u; }
   using Base = OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1>;
   static constexpr int S = S_, I = I_;
   static_assert(!Sys::reads_d, "views of this kernel carry the fresh k[0] where the reference carries the stale d");
@@ -92,7 +105,9 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
   uint32_t has_last_call, status;
   bool combined;  // k[1 .. I-1] of the step in flight already hold the interpolant coefficients
   unsigned n_steps, n_events, n_evlog, n_samples;
-  unsigned long long n_rhs, on_step_calls;
+  unsigned n_make, n_k0;  // make_step calls and k[0] evaluations: rhs_evals = S n_make + n_k0
+  unsigned step_limit;    // max_steps as a 32-bit bound (0xFFFFFFFF = none), set once per kernel
+  unsigned long long on_step_calls;
   unsigned n_iters;  // location-loop iterations of this member (dfb_totals.locate_iters)
 
   __device__ explicit OdeEventStepper(const OdeFixedArgs& A_) : Base(A_) {}
@@ -278,6 +293,32 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
     return fmax(lft, rgt);
   }
 
+  // Bisection (loc.rs:235-259) of locator LI of a SPEC build: the detector id is a constant
+  template <int LI>
+  __device__ double locate_spec() {
+    constexpr int id = spec_id(LI);
+    double lft = t_prev, rgt = t_curr;
+    if (Sys::detector(id, view_curr(), prm()) < 0.0) {
+      lft = t_curr;
+      rgt = t_prev;
+    }
+    double w = fabs(rgt - lft);
+    double w_prev = 2.0 * w;
+    double m = 0.5 * (lft + rgt);
+#pragma unroll 1
+    while (w < w_prev) {
+      w_prev = w;
+      double y[N];
+      eval_in_step<0>(m, y);
+      if (Sys::detector(id, Ref{m, y, y, m, y, &this->nohist}, prm()) < 0.0) lft = m;
+      else rgt = m;
+      m = 0.5 * (lft + rgt);
+      w = fabs(rgt - lft);
+      ++n_iters;
+    }
+    return fmax(lft, rgt);
+  }
+
   // Filter state machines (loc.rs:613-688); l is a compile-time index after unrolling
   __device__ __forceinline__ bool filter_pass(const dfb_locator& L, int l, double t) {
     switch (L.filter) {
@@ -318,14 +359,17 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
 #pragma unroll
     for (int l = 0; l < NLOC; ++l) {
       const dfb_locator& L = A.loc[l];
-      const double c = Sys::detector(L.detector_id, view_curr(), prm());
-      const double p = Sys::detector(L.detector_id, view_prev(), prm());
+      const int id = HAS_SPEC ? spec_id(l) : L.detector_id;
+      const int kind = HAS_SPEC ? spec_detection(l) : L.detection;
+      const double c = Sys::detector(id, view_curr(), prm());
+      const double p = Sys::detector(id, view_prev(), prm());
       const bool up = (c > 0.0) & (p <= 0.0);      // AboveZero (loc.rs:130-132)
       const bool down_z = (c <= 0.0) & (p > 0.0);  // the falling half of Zero (loc.rs:127-129)
       const bool down = (c < 0.0) & (p >= 0.0);    // BelowZero (loc.rs:133-135)
-      const bool det = L.detection == DFB_DET_ZERO ? (up | down_z) : (L.detection == DFB_DET_ABOVE_ZERO ? up : down);
-      const bool suppressed = (L.dedup != 0) & (((has_last_call >> l) & 1u) != 0u) & !(t_prev > last_call[l]);
-      fired |= ((l < A.n_loc) & det & !suppressed) ? (1u << l) : 0u;
+      const bool det = kind == DFB_DET_ZERO ? (up | down_z) : (kind == DFB_DET_ABOVE_ZERO ? up : down);
+      const bool dedup = HAS_SPEC ? spec_dedup(l) : (L.dedup != 0);
+      const bool suppressed = dedup & (((has_last_call >> l) & 1u) != 0u) & !(t_prev > last_call[l]);
+      fired |= ((HAS_SPEC || l < A.n_loc) & det & !suppressed) ? (1u << l) : 0u;
     }
     return fired;
   }
@@ -363,7 +407,7 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
     // branch-free: two return paths made the compiler duplicate the (predicated) register copies
     // that follow each call site
     const bool more = t_curr < A.t1;
-    const bool limit = more && A.max_steps > 0 && (long long)n_steps >= A.max_steps;
+    const bool limit = more && n_steps >= step_limit;
     status |= limit ? uint32_t(DFB_TRAJ_STEP_LIMIT) : 0u;
     return (more && !limit) ? MODE_STEP : MODE_DONE;
   }
@@ -399,7 +443,8 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
       sep_prev[l] = on_times ? 0.0 : -1.7976931348623157e308;  // T::min_value() / list position
     }
     n_steps = n_events = n_evlog = n_samples = n_iters = 0u;
-    n_rhs = on_step_calls = 0ull;
+    n_make = n_k0 = 0u;
+    on_step_calls = 0ull;
     if (A.on_start_cb != DFB_CB_NONE) {  // events_on_start.eval_mut (solver.rs:289)
       RefMut m{&t_curr, p_curr(), d_curr(), t_prev, p_prev(), &this->nohist};
       Sys::callback(A.on_start_cb, m, prm(), aux);
@@ -425,7 +470,7 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
     }
     A.steps[gid] = n_steps;
     A.events[gid] = n_events;
-    A.rhs_evals[gid] = n_rhs;
+    A.rhs_evals[gid] = (unsigned long long)n_make * S + n_k0;
     A.status[gid] = st;
     if (A.locate_iters) A.locate_iters[gid] = n_iters;
     if (A.n_events) A.n_events[gid] = n_evlog;
@@ -440,6 +485,7 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
     int ev_index = 0;
     uint32_t fired_mask = 0u;
     int parked_iters = 0;  // warp-uniform: step rounds since the first lane parked
+    step_limit = A.max_steps > 0 ? (A.max_steps >= 0xFFFFFFFFll ? 0xFFFFFFFFu : unsigned(A.max_steps)) : 0xFFFFFFFFu;
 
     while (true) {
       // finished lanes hand in their member and pull the next one
@@ -465,14 +511,29 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
           bool found = false;
           double best_t = 0.0;
           int best_i = 0;
-#pragma unroll
-          for (int l = 0; l < NLOC; ++l) {
-            if (l < A.n_loc && ((fired_mask >> l) & 1u)) {
-              const double tl = locate_base(A.loc[l]);
+          if (HAS_SPEC) {
+            if (NLOC > 0 && (fired_mask & 1u)) {
+              best_t = locate_spec<0>();
+              found = true;
+            }
+            if (NLOC > 1 && (fired_mask & 2u)) {
+              const double tl = locate_spec<(NLOC > 1 ? 1 : 0)>();
               if (!found || tl < best_t) {  // strictly earliest, first index wins ties
                 found = true;
                 best_t = tl;
-                best_i = l;
+                best_i = 1;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int l = 0; l < NLOC; ++l) {
+              if (l < A.n_loc && ((fired_mask >> l) & 1u)) {
+                const double tl = locate_base(A.loc[l]);
+                if (!found || tl < best_t) {  // strictly earliest, first index wins ties
+                  found = true;
+                  best_t = tl;
+                  best_i = l;
+                }
               }
             }
           }
@@ -515,11 +576,11 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
             const double h_req = restep ? (ev_time - t_curr) : fmin(A.h, A.t1 - t_curr);
             if (t_prev == t_curr) {  // state.rs:97-98: make_step evaluates k[0] itself
               Sys::rhs(view_curr(), prm(), d_curr());
-              ++n_rhs;
+              ++n_k0;
             }
             this->template step<false>(h_req);
             combined = false;
-            n_rhs += S;
+            ++n_make;
             if (restep) {
               // solver.rs:304-309: commit; zero step; callback of the located event; commit
               t_prev = t_curr;
@@ -529,7 +590,7 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
               for (int l = 0; l < NLOC; ++l) {
                 if (l == ev_index) {
                   const dfb_locator& L = A.loc[l];
-                  if (L.dedup) {  // DedupLocF::eval_mut (loc.rs:1023-1026)
+                  if (HAS_SPEC ? spec_dedup(l) : (L.dedup != 0)) {  // DedupLocF::eval_mut (loc.rs:1023-1026)
                     has_last_call |= 1u << l;
                     last_call[l] = t_curr;
                   }
@@ -582,10 +643,10 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
 #define DFB_EV_MINB(N) ((N) <= 2 ? 4 : 3)
 #endif
 template <class Sys, int S, int I, unsigned long long AMASK, unsigned BMASK, bool FAST, int NLOC, int BLOCK,
-          bool SIMPLE = false, bool LEAN = false>
+          bool SIMPLE = false, bool LEAN = false, unsigned SPEC = kEvSpecRuntime>
 __global__ void __launch_bounds__(BLOCK, DFB_EV_MINB(Sys::N))
     ode_event_kernel(const __grid_constant__ OdeFixedArgs A) {
-  OdeEventStepper<Sys, S, I, AMASK, BMASK, FAST, NLOC, SIMPLE, LEAN> st(A);
+  OdeEventStepper<Sys, S, I, AMASK, BMASK, FAST, NLOC, SIMPLE, LEAN, SPEC> st(A);
   st.run();
 }
 

@@ -21,6 +21,37 @@ void launch_grid(Kernel kernel, const OdeFixedArgs& A, int n_sm, cudaStream_t st
   kernel<<<unsigned(grid ? grid : 1), kBlock, 0, stream>>>(A);
 }
 
+// Locator sets known at compile time (dev/ode_event.cuh, SPEC): the shipped event examples.  Any other set
+// of plain sign-change locators runs the same kernel with the descriptors read at run time.
+template <class Sys>
+struct EventSpec {
+  static constexpr int n_loc = 0;
+  static constexpr unsigned spec = kEvSpecRuntime;
+};
+#ifndef DFB_PLUGIN_SYSTEM
+template <>
+struct EventSpec<SysBouncingBall> {  // examples/bouncing-ball.rs:27-32: on(zero(dx)), on_mut(below_zero(x), ..)
+  static constexpr int n_loc = 2;
+  static constexpr unsigned spec = ev_spec_byte(1, DFB_DET_ZERO, true) | (ev_spec_byte(2, DFB_DET_BELOW_ZERO, true) << 8);  // detector ids: dx = 1, x = 2
+};
+template <>
+struct EventSpec<SysEggBilliard> {  // examples/egg-billiard.rs:22: on_mut(above_zero(boundary), ..)
+  static constexpr int n_loc = 1;
+  static constexpr unsigned spec = ev_spec_byte(1, DFB_DET_ABOVE_ZERO, true);
+};
+template <>
+struct EventSpec<SysRelayMsign> {  // examples/ode-2-relay-msign.rs:21: on(zero(x))
+  static constexpr int n_loc = 1;
+  static constexpr unsigned spec = ev_spec_byte(1, DFB_DET_ZERO, true);
+};
+#endif
+inline unsigned spec_of(const OdeFixedArgs& A) {
+  unsigned v = 0u;
+  for (int l = 0; l < A.n_loc && l < 4; ++l)
+    v |= ev_spec_byte(A.loc[l].detector_id, A.loc[l].detection, A.loc[l].dedup != 0) << (8 * l);
+  return v;
+}
+
 template <class Sys, int S, int I>
 bool try_launch(int S_rt, int I_rt, const OdeFixedArgs& A, int n_sm, cudaStream_t stream, int* rc) {
   if (S_rt != S || I_rt != I) return false;
@@ -36,6 +67,16 @@ bool try_launch(int S_rt, int I_rt, const OdeFixedArgs& A, int n_sm, cudaStream_
   }
   if constexpr (S == 7) {
     const bool lean = A.trace_every == 0 && !getenv("DFB_EVENT_NO_LEAN");  // no Trace policy: LEAN build
+    if constexpr (kFast && EventSpec<Sys>::n_loc > 0) {
+      using ES = EventSpec<Sys>;
+      bool match = simple && lean && A.n_loc == ES::n_loc && spec_of(A) == ES::spec && !getenv("DFB_EVENT_RUNTIME_SPEC");
+      for (int l = 0; l < A.n_loc && match; ++l) match = A.loc[l].detector_id >= 0 && A.loc[l].detector_id < 16;
+      if (match) {
+        launch_grid(ode_event_kernel<Sys, S, I, AM, BM, kFast, ES::n_loc, kBlock, true, true, ES::spec>, A, n_sm, stream);
+        *rc = int(cudaGetLastError());
+        return true;
+      }
+    }
     if (simple && A.n_loc <= 1) {
       if (lean) launch_grid(ode_event_kernel<Sys, S, I, AM, BM, kFast, 1, kBlock, true, true>, A, n_sm, stream);
       else launch_grid(ode_event_kernel<Sys, S, I, AM, BM, kFast, 1, kBlock, true>, A, n_sm, stream);

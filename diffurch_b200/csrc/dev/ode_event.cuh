@@ -28,6 +28,9 @@
 #ifndef DFB_EV_EAGER_MAX_N
 #define DFB_EV_EAGER_MAX_N 2
 #endif
+#ifndef DFB_EV_SPEC_PAIRED
+#define DFB_EV_SPEC_PAIRED 0  // two bisection iterations per round (3 evaluations): measured slower, see locate_spec
+#endif
 #ifndef DFB_EV_UNROLL
 #define DFB_EV_UNROLL 1
 #endif
@@ -293,29 +296,64 @@ struct OdeEventStepper : OdeFixedStepper<Sys, S_, AMASK, BMASK, false, 1> {
     return fmax(lft, rgt);
   }
 
-  // Bisection (loc.rs:235-259) of locator LI of a SPEC build: the detector id is a constant
+  // Bisection (loc.rs:235-259) of locator LI of a SPEC build: the detector id is a constant.
+  // DFB_EV_SPEC_PAIRED=1 (experiment, off): two iterations per round — next to f(m) the round evaluates f at
+  // BOTH midpoints the following iteration could ask for, 0.5 (m + rgt) and 0.5 (lft + m), same expressions on
+  // the same operands, so brackets, midpoints and iteration count are bit for bit those of the one-at-a-time
+  // loop, and the three interpolations are independent instruction streams.  Measured: egg billiard 14.6 ->
+  // 16.7 ms, bouncing ball 5.43 -> 5.60 ms — with all 32 lanes of a batched location round active and four
+  // warps per scheduler the loop is bound by FP64 throughput, not by its dependent chain, and the third
+  // evaluation is pure extra work (profiles/r2_event_kernel_tuning.txt).
+  template <int LI>
+  __device__ __forceinline__ double spec_fn(double t) {
+    double y[N];
+    eval_in_step<0>(t, y);
+    return Sys::detector(spec_id(LI), Ref{t, y, y, t, y, &this->nohist}, prm());
+  }
   template <int LI>
   __device__ double locate_spec() {
-    constexpr int id = spec_id(LI);
     double lft = t_prev, rgt = t_curr;
-    if (Sys::detector(id, view_curr(), prm()) < 0.0) {
+    if (Sys::detector(spec_id(LI), view_curr(), prm()) < 0.0) {
       lft = t_curr;
       rgt = t_prev;
     }
     double w = fabs(rgt - lft);
     double w_prev = 2.0 * w;
     double m = 0.5 * (lft + rgt);
+#if DFB_EV_SPEC_PAIRED
 #pragma unroll 1
     while (w < w_prev) {
       w_prev = w;
-      double y[N];
-      eval_in_step<0>(m, y);
-      if (Sys::detector(id, Ref{m, y, y, m, y, &this->nohist}, prm()) < 0.0) lft = m;
+      const double m_l = 0.5 * (m + rgt);  // the next midpoint if lft = m
+      const double m_r = 0.5 * (lft + m);  // ... if rgt = m
+      const double f_m = spec_fn<LI>(m), f_l = spec_fn<LI>(m_l), f_r = spec_fn<LI>(m_r);
+      const bool left = f_m < 0.0;
+      lft = left ? m : lft;
+      rgt = left ? rgt : m;
+      const double m2 = left ? m_l : m_r;
+      const double f2 = left ? f_l : f_r;
+      w = fabs(rgt - lft);
+      ++n_iters;
+      m = m2;
+      if (!(w < w_prev)) break;
+      w_prev = w;
+      if (f2 < 0.0) lft = m2;
+      else rgt = m2;
+      m = 0.5 * (lft + rgt);
+      w = fabs(rgt - lft);
+      ++n_iters;
+    }
+#else
+#pragma unroll 1
+    while (w < w_prev) {
+      w_prev = w;
+      if (spec_fn<LI>(m) < 0.0) lft = m;
       else rgt = m;
       m = 0.5 * (lft + rgt);
       w = fabs(rgt - lft);
       ++n_iters;
     }
+#endif
     return fmax(lft, rgt);
   }
 

@@ -472,7 +472,10 @@ struct OdeFixedPeriodicStepper : OdeFixedStepper<Sys, S, AMASK, BMASK, PRESCALED
           const double fl_curr = floor((t_next - L.offset) / L.period);
           const double bound = (fl_curr + 1.0) * L.period + L.offset;
           const double q = bound - 1e-9 * (fabs(bound) + fabs(L.offset) + fabs(L.period));
-          quiet = (L.period > 0.0 && q < quiet) ? q : ((L.period > 0.0) ? quiet : -inf);
+          // (a locator without DedupLocF may fire again on the step that starts AT its event time when
+          // floor() rounds down there — solver.rs does — so only deduplicated locators may be skipped)
+          const bool skippable = L.period > 0.0 && L.dedup != 0;
+          quiet = skippable ? (q < quiet ? q : quiet) : -inf;
           if (L.dedup && ((has_last_call >> l) & 1u) && !(t_curr > last_call[l])) continue;
           if (fl_prev < fl_curr) {
             const double tl = fl_curr * L.period + L.offset;

@@ -5,11 +5,13 @@
 // a member's own state is the same for every member: the time grid, the window position
 // (w, tw0, tw1), the replay of the prune, the loop control, the prefetch bookkeeping, and the
 // ~50 tableau / interpolant constants that do not fit the 63 uniform registers and are re-fetched
-// from the constant bank every step.  dde_fixed_kernel pays all of that per member (ncu: 355
-// instructions per member-step, 72 % of the issue slots — it is issue-bound, not HBM-bound, since
+// from the constant bank every step.  Round 1's dde_fixed_kernel paid all of that per member (ncu: 355
+// instructions per member-step, 72 % of the issue slots — issue-bound, not HBM-bound, since
 // the records shrank to 40 B).  Here a thread integrates TPT members (trajectory g and
 // g + grid threads): the shared part is paid once per TPT members and the TPT independent
-// dependency chains interleave, as in ode_fixed.cuh.
+// dependency chains interleave, as in ode_fixed.cuh.  (Round 2 cut the one-member kernel's shared part
+// instead — lean steady loop, ~280 instructions per member-step — and it now wins at most sizes; the
+// launcher chooses per ensemble size, see kernels_dde_fixed.cu.)
 //
 // A warp whose members do not all share one delay (or whose second slot runs past the end of the
 // ensemble) is handed, slot by slot, to the one-member stepper of dde_fixed.cuh inside the same

@@ -39,10 +39,12 @@ bool try_launch(int S_rt, int I_rt, unsigned long long am, unsigned bm, unsigned
                 const DdeFixedArgs& A, cudaStream_t stream, int* rc) {
   if (S_rt != S || I_rt != I) return false;
   if ((am & ~AMASK) || (bm & ~BMASK) || (bim & ~BIMASK)) return false;
-  // Members per thread and block size from the ensemble size.  The kernel is HBM-bound once the device
-  // is full (two members per thread: dev/dde_fixed2.cuh) and latency-bound below that: a small ensemble
-  // (a 2^18-member ensemble sharded over 8 GPUs is 1 024 warps for 592 SM sub-partitions) is spread over
-  // every SM in 32-thread blocks, one member per thread.  DFB_DDE_TPT=1|2 / DFB_DDE_BLOCK override (tuning).
+  // Members per thread and block size from the ensemble size.  The kernel is HBM-bound once the device is
+  // full and latency-bound below that (a 2^18-member ensemble sharded over 8 GPUs is 1 024 warps for 592 SM
+  // sub-partitions).  Two builds: one member per thread (dev/dde_fixed.cuh, PRE: delayed values ahead of the
+  // stage chain, lean steady loop, 8 staging slots) and two per thread (dev/dde_fixed2.cuh); the wave/tail
+  // model below picks.  Small ensembles are spread over every SM in 32- or 64-thread blocks.
+  // DFB_DDE_TPT=1|2 / DFB_DDE_BLOCK / DFB_DDE_RELAXED override (tuning, tests).
   using Stepper = DdeFixedStepper<Sys, S, I, AMASK, BMASK, BIMASK>;
   auto kernel2 = dde_fixed2_kernel<Sys, S, I, AMASK, BMASK, BIMASK, kBlock, kMinBlocks2>;
   auto kernel1 = dde_fixed_kernel<Sys, S, I, AMASK, BMASK, BIMASK, kBlock, kMinBlocks>;

@@ -344,6 +344,16 @@ int launch_general(dfb_handle* h, const DevProblem& P, cudaStream_t stream) {
               "no compiled kernel for this (system, tableau shape): see kernels_general.cu");
 }
 
+// Every propagated discontinuity inside the retained window is a located event, i.e. two extra history
+// records (solver.rs:304,308), and with several delays the breaking points t_i + tau_j pile up: the default
+// ring leaves room for as many as the per-member discontinuity list can hold (found by the fuzz campaign,
+// seed 125 at DFB_FUZZ_SCALE=8: delays 0.5 and 0.8 with h = 0.75 overflowed a 32-record ring).
+size_t propagation_slack(const dfb_problem* desc) {
+  for (int l = 0; l < desc->n_loc; ++l)
+    if (desc->loc[l].kind == DFB_LOC_PROPAGATION) return 2 * size_t(DFB_DISCO_CAP);
+  return 0;
+}
+
 // History rings of the general kernel (reference record format: t, y, k[S]).
 int alloc_general_rings(dfb_handle* h) {
   if (h->d_ring_t) return DFB_OK;
@@ -357,7 +367,7 @@ int alloc_general_rings(dfb_handle* h) {
     double hmin = desc->stepsize_kind == DFB_STEP_AUTOMATIC ? desc->automatic.stepsize_min : desc->h;
     double want = std::isfinite(desc->max_delay) && hmin > 0 ? std::ceil(desc->max_delay / hmin) : 1024.0;
     if (!(want < 1e6)) want = 1e6;
-    cap = size_t(want) * 2 + 16;
+    cap = size_t(want) * 2 + 16 + propagation_slack(desc);
   }
   cap = next_pow2(cap);
   if (cap > (1u << 20)) return fail(DFB_ERR_INVALID, "history ring capacity too large; set ring_capacity explicitly");
@@ -620,7 +630,7 @@ int dfb_create(const dfb_problem* desc, size_t n_traj, int device, dfb_handle** 
       if (cap == 0) {  // as for the general rings below
         double want = std::isfinite(desc->max_delay) && desc->h > 0 ? std::ceil(desc->max_delay / desc->h) : 1024.0;
         if (!(want < 1e6)) want = 1e6;
-        cap = size_t(want) * 2 + 16;
+        cap = size_t(want) * 2 + 16 + propagation_slack(desc);
       }
       cap = next_pow2(cap);
       // one ring column per resident thread (members are assigned dynamically): never more than the

@@ -486,7 +486,9 @@ struct OdeFixedPeriodicStepper : OdeFixedStepper<Sys, S, AMASK, BMASK, PRESCALED
             }
           }
         }
-        t_quiet = quiet;
+        // the bounds assume the whole step (t_curr, t_next] is taken; when an event cuts it short another
+        // locator's boundary may still lie ahead inside it: decide exactly again after the event
+        t_quiet = found ? -inf : quiet;
       }
       if (found && best_t >= t_curr) {  // solver.rs:299-307
         n_rhs += S + 1;  // the undone full step and the k[0] make_step re-evaluates after undo_step

@@ -1070,6 +1070,29 @@ def test_periodic_kernel_quiet_interval_same_events_as_oracle(oracle, h, period,
     assert np.array_equal(hot.p, o.p) and np.array_equal(hot.t, o.t)
 
 
+def test_periodic_kernel_two_boundaries_inside_one_step(oracle):
+    # two Periodic locators whose boundaries regularly fall inside the SAME step: the event of the earlier one
+    # cuts the step short and the later one's boundary still lies ahead — the quiet-interval bound computed for
+    # the whole step must not survive the cut (regression: fuzz seed 110 at DFB_FUZZ_SCALE=8 lost those events)
+    lam = np.array([-0.3, 0.2, 0.05, -0.01]).reshape(-1, 1)
+    for h, p1, o1, p2 in ((0.1, 0.25, 0.03, 0.375), (0.0123456789, 0.05, 0.004, 0.075), (0.5, 0.3, 0.1, 0.45)):
+        def mk():
+            return (d.Solver.new().initial(np.ones((4, 1))).interval(0.0, 40.0 * h).stepsize(h)
+                    .equation(d.systems.Linear1, lam)
+                    .on_mut(d.Periodic(p1, o1), "renormalize").on_mut(d.Periodic(p2, 0.0), "renormalize")
+                    .log_events(d.EventLog(1024)))
+        hot = mk().run()
+        assert hot.totals["kernel_kind"] == KERNEL_ODE_FIXED_PERIODIC
+        o = oracle.run_solver(mk(), n_threads=2)
+        assert_same_counters(hot, o)
+        assert np.array_equal(hot.event_n, o.event_n) and int(hot.event_n[0]) > 10
+        ne = min(int(hot.event_n[0]), 1024)
+        assert np.array_equal(hot.event_t[:, :ne], o.event_t[:, :ne])
+        assert np.array_equal(hot.event_index[:, :ne], o.event_index[:, :ne])
+        assert np.array_equal(hot.p, o.p) and np.array_equal(hot.t, o.t)
+        assert np.max(np.abs(hot.aux - o.aux)) < 1e-12
+
+
 def test_periodic_kernel_stop_integration_is_per_lane(oracle):
     # the egg-billiard reflection callback (examples/egg-billiard.rs:22-38) on a Periodic clock: member
     # i calls stop_integration at its (i % 7 + 1)-th event, so lanes of one warp stop at different

@@ -478,7 +478,8 @@ def test_dde_hot_path_builds_agree_lean_loop(oracle):
     # bits among themselves, the oracle's step grid, the FAST tolerance against the oracle's state.  Delays from
     # 6 to 200 steps put the window anywhere from right behind the write head to the far end of the ring.
     k = 0.5 + np.arange(133) / 132.0                       # ragged: 4 warps + 5 members
-    for tau, h, t1 in ((1.0, 0.02, 25.0), (0.3, 0.05, 30.0), (2.0, 0.01, 12.0), (1.0, 0.037, 20.0)):
+    for tau, h, t1 in ((1.0, 0.02, 25.0), (0.3, 0.05, 30.0), (2.0, 0.01, 12.0), (1.0, 0.037, 20.0),
+                       (1.0, 0.0123456789, 120.0), (0.77, 0.1, 400.0)):   # ~10^4 and 4000 steps: many window slides
         mk = lambda arith: (d.Solver.new().max_delay(tau).initial(d.InitFn(d.SIN)).interval(0.0, t1).stepsize(h)
                             .equation(d.systems.DdeLinear, cases.dde_params(k, tau)).arith(arith))
         o = oracle.run_solver(mk("strict"), n_threads=8)
@@ -493,7 +494,7 @@ def test_dde_hot_path_builds_agree_lean_loop(oracle):
                     del os.environ[e]
             assert g.totals["kernel_kind"] == d.abi.KERNEL_DDE_FIXED and np.all(g.status == 0), name
             assert np.array_equal(g.steps, o.steps) and np.array_equal(g.t, o.t), name
-            assert np.max(np.abs(g.p - o.p)) < 1e-10, (name, tau, h)
+            assert np.max(np.abs(g.p - o.p)) < 1e-9, (name, tau, h)
             runs[name] = g
         assert np.array_equal(runs["pre"].p, runs["capped"].p), (tau, h)
         assert np.array_equal(runs["pre"].p, runs["two"].p), (tau, h)

@@ -168,6 +168,9 @@ static __device__ __noinline__ LookupValue<N> ring_lookup_slow(const DdeEventArg
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
+#ifndef DFB_DDE_EV_PRE
+#define DFB_DDE_EV_PRE 0  // delayed values of a step looked up ahead of its stage chain: measured slower (see PreHist)
+#endif
 #ifndef DFB_DDE_EV_PREFETCH
 #define DFB_DDE_EV_PREFETCH 1
 #endif
@@ -448,6 +451,41 @@ struct DdeEventStepper {
   __device__ __forceinline__ Ref view_curr() { return Ref{t_curr, p_curr, d_curr, t_prev, p_prev, &hist}; }
   __device__ __forceinline__ Ref view_prev() { return Ref{t_prev, p_prev, k[0], t_prev, p_prev, &hist}; }
 
+  // History of the views handed to the right-hand side when the system's one delay is constant
+  // (Sys::has_const_delay): the delayed values of the whole step are looked up BEFORE its stage chain — their
+  // times t_prev + c_i h - tau do not depend on the state — so the S ring reads (L1 / L2 / HBM latency each)
+  // overlap instead of standing one after the other inside the stages.  The functor still calls
+  // s.p_at(s.t - tau): it is handed the value computed for that very time and the ring for any other.
+  // EXPERIMENT, off (DFB_DDE_EV_PRE=0): what pays for a lone warp of the constant-delay kernel (dde_fixed.cuh)
+  // costs here — relay-clamp 2^16 / 2^18 members 9.47 -> 10.07 / 34.2 -> 38.4 ms: with 16 warps per SM the
+  // ring reads are already overlapped by other warps, and the S values held across the stage chain push a
+  // kernel that spills at 128 registers further (profiles/r2_dde_event_tuning.txt).
+  struct PreHist {
+    Hist* h;
+    double t_key;
+    const double* val;
+    template <int D>
+    __device__ __forceinline__ void eval(double t, double* out) {
+      if (D == 0 && t == t_key) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) out[n] = val[n];
+      } else {
+        h->template eval<D>(t, out);
+      }
+    }
+  };
+  static constexpr bool PRE = (DFB_DDE_EV_PRE != 0) && Sys::has_const_delay;
+
+  template <bool P = PRE>
+  __device__ __forceinline__ void rhs_stage(double t_key, const double* val, double* out) {
+    if constexpr (P) {
+      PreHist ph{&hist, t_key, val};
+      Sys::rhs(StateRef<N, PreHist>{t_curr, p_curr, d_curr, t_prev, p_prev, &ph}, prm, out);
+    } else {
+      Sys::rhs(view_curr(), prm, out);
+    }
+  }
+
   // ---- State::make_step (state.rs:94-120); the caller guarantees d_curr is current --------
   __device__ __forceinline__ void make_step(double t_step) {
 #pragma unroll
@@ -456,6 +494,16 @@ struct DdeEventStepper {
       p_prev[n] = p_curr[n];
     }
     t_prev = t_curr;
+    double pre_t[PRE ? S : 1], pre_p[PRE ? S : 1][N];  // slot i-1 = stage i, slot S-1 = the step end
+    if constexpr (PRE) {
+      const double tau = Sys::const_delay(prm);
+#pragma unroll
+      for (int i = 1; i <= S; ++i) {
+        const double tt = (i < S ? t_prev + A.c[i] * t_step : t_prev + t_step) - tau;
+        pre_t[PRE ? i - 1 : 0] = tt;
+        hist.template eval<0>(tt, pre_p[PRE ? i - 1 : 0]);
+      }
+    }
 #pragma unroll
     for (int i = 1; i < S; ++i) {
       t_curr = t_prev + A.c[i] * t_step;
@@ -466,7 +514,7 @@ struct DdeEventStepper {
         for (int j = 0; j < i; ++j) acc = acc + k[j][n] * A.a[i * DFB_MAX_STAGES + j];
         p_curr[n] = p_prev[n] + acc * t_step;
       }
-      Sys::rhs(view_curr(), prm, k[i]);
+      rhs_stage(pre_t[PRE ? i - 1 : 0], pre_p[PRE ? i - 1 : 0], k[i]);
     }
 #pragma unroll
     for (int n = 0; n < N; ++n) {
@@ -476,7 +524,7 @@ struct DdeEventStepper {
       p_curr[n] = p_prev[n] + acc * t_step;
     }
     t_curr = t_prev + t_step;
-    Sys::rhs(view_curr(), prm, d_curr);
+    rhs_stage(pre_t[PRE ? S - 1 : 0], pre_p[PRE ? S - 1 : 0], d_curr);
     n_rhs += S;
     // pre-combined interpolant: cf_j = sum_i k_i bi[i][j] / t_step^(j-1)  (needs b_i(0) = 0: host-checked)
     t_slide = hist.t_look;

@@ -401,6 +401,8 @@ struct SysDdeRelayClamp : SysBase {  // examples/dde-relay-clamp.rs:24-35
   static constexpr bool uses_history = true;
   static constexpr bool pure_rhs = false;
   static constexpr bool pure_detectors = true;
+  static constexpr bool has_const_delay = true;  // rhs looks the history up at s.t - const_delay(prm) only
+  __device__ __forceinline__ static double const_delay(const double* prm) { return prm[2]; }
   template <class V>
   __device__ __forceinline__ static void rhs(const V& s, const double* prm, double* out) {
     const double x = s.p[0], dx = s.p[1];

@@ -51,7 +51,7 @@ WORKLOAD = "lorenz_2^20_members_rho_sweep_rktp64_h=1/250_t=[0,50]"
 DDE_MEMBERS = 1 << 18
 DDE_STEPS_PER_MEMBER = 5001
 DDE_WORKLOAD = "dde_linear_2^18_members_k_sweep_tau=1_rktp64_h=0.02_t=[0,100]"
-DDE_DRAM_TRAFFIC_PER_LAUNCH = 50509854000 + 51415350000  # ncu --set full, profiles/r1_final_ncu_full_dde_fixed.txt
+DDE_DRAM_TRAFFIC_PER_LAUNCH = 48981858000 + 50912352000  # ncu --set full, profiles/r2_final_ncu_full_dde_fixed.txt
 # Algorithmic bytes per RK step: one coefficient record (y, d_1..d_4) = 40 B written + one read (N=1, I=5).
 # SURVEY.md §8(d) quotes 48 B records (96 B/step) because it counts the record's start time; with a fixed
 # step the time grid is regenerated, so the start time carries no information and is not stored.  The
@@ -412,7 +412,7 @@ def dde_report(local, ctx, total, K, scaling):
                      "frac": achieved / hbm,
                      "traffic": DDE_DRAM_TRAFFIC_PER_LAUNCH if (world == 1 and members_total == DDE_MEMBERS) else None,
                      "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one 2^18-member "
-                                       "launch, profiles/r1_final_ncu_full_dde_fixed.txt (algorithmic bytes per launch: "
+                                       "launch, profiles/r2_final_ncu_full_dde_fixed.txt (algorithmic bytes per launch: "
                                        f"{int(DDE_BYTES_PER_STEP * steps // world)})",
                      "peak_source": src, "per_gpu": True,
                      "algorithmic_bytes_per_rk_step": DDE_BYTES_PER_STEP,

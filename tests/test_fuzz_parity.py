@@ -122,6 +122,19 @@ def test_fuzz_fixed_step_ode_strict_bit_exact(oracle, seed):
         assert np.max(np.abs(g.aux - o.aux)) <= 1e-12 * (1.0 + np.max(np.abs(o.aux))), what
         g.aux = o.aux
     same(g, o, what)
+    if periodic:
+        # the same problem in FAST arithmetic (pre-scaled / folded stages, predicted Periodic events): the event
+        # protocol is time-grid arithmetic, so every counter and the final time are the oracle's; the state and
+        # the accumulated logarithms within the FAST tolerance (linear systems: no chaotic amplification)
+        f = mk().arith("fast").run()
+        assert f.totals["kernel_kind"] == g.totals["kernel_kind"], what
+        for name in ("steps", "events", "rhs_evals", "status"):
+            assert np.array_equal(getattr(f, name), getattr(o, name)), f"{name} differs {what} fast"
+        assert np.array_equal(f.t, o.t), what
+        scale = np.maximum(np.abs(o.p), 1.0)
+        assert np.max(np.abs(f.p - o.p) / scale) < 1e-10, what + " fast"
+        if o.aux is not None and np.size(o.aux):
+            assert np.max(np.abs(f.aux - o.aux)) < 1e-9 * (1.0 + np.max(np.abs(o.aux))), what + " fast"
 
 
 DETECTIONS = [abi.DET_ZERO, abi.DET_ABOVE_ZERO, abi.DET_BELOW_ZERO, abi.DET_POSITIVE, abi.DET_NEGATIVE,

@@ -303,6 +303,31 @@ def test_event_kernel_strict_equals_general_kernel_and_oracle(oracle, case):
     assert np.array_equal(hot.event_t, o.event_t) and np.array_equal(hot.p, o.p)
 
 
+def test_event_kernel_compile_time_locators_match_run_time_descriptors(oracle):
+    # FAST builds of the shipped event examples know their locators at compile time (SPEC: detector id,
+    # detection kind, DedupLocF folded into the kernel); DFB_EVENT_RUNTIME_SPEC=1 runs the same problems with the
+    # descriptors read per step.  Same arithmetic either way: identical bits, and the oracle's event sequence.
+    def relay():   # examples/ode-2-relay-msign.rs:15-26 without its Trace (a traced problem is not a LEAN/SPEC build)
+        return (d.Solver.new().initial(np.tile([0.25, 0.0], (40, 1)) + 0.01 * np.arange(40).reshape(-1, 1))
+                .equation(d.systems.RelayMsign).interval(0.5, 10.5).stepsize(0.09)
+                .on(d.Locator.zero("x"), None).log_events(d.EventLog(64)))
+    for mk in (lambda: cases.bouncing_ball(n=70, t1=6.0), lambda: cases.egg_billiard(n=70, reflections=12), relay):
+        spec = mk().arith("fast").run()
+        os.environ["DFB_EVENT_RUNTIME_SPEC"] = "1"
+        try:
+            rt = mk().arith("fast").run()
+        finally:
+            del os.environ["DFB_EVENT_RUNTIME_SPEC"]
+        assert spec.totals["kernel_kind"] == KERNEL_ODE_EVENT and rt.totals["kernel_kind"] == KERNEL_ODE_EVENT
+        _same_everything(spec, rt)
+        if mk is relay:   # a relay chatters around x = 0: FAST rounding may legitimately re-order its crossings
+            continue
+        o = oracle.run_solver(mk().arith("strict"), n_threads=4)
+        assert np.array_equal(spec.event_n, o.event_n) and np.array_equal(spec.event_index, o.event_index)
+        assert np.array_equal(spec.steps, o.steps) and np.array_equal(spec.events, o.events)
+        assert np.nanmax(np.abs(spec.event_t - o.event_t)) < 1e-9
+
+
 def test_event_kernel_dynamic_assignment_ragged_costs(oracle):
     # members stop after very different numbers of reflections (1 .. 97), far more members than one
     # block: lanes hand in finished members and pull new ones from the work counter; results are

@@ -444,7 +444,8 @@ struct DdeEventStepper {
   uint32_t det_valid, det_valid_prev;
   uint32_t has_last_call;
   unsigned n_steps, n_events, n_evlog, n_samples, n_iters, on_step_calls;
-  unsigned long long n_rhs;
+  unsigned n_make, n_k0;  // make_step calls and k[0] evaluations: rhs_evals = S n_make + n_k0
+  unsigned step_limit;    // max_steps as a 32-bit bound (0xFFFFFFFF = none), set once per kernel
 
   __device__ explicit DdeEventStepper(const DdeEventArgs& A_) : A(A_) {}
 
@@ -525,7 +526,7 @@ struct DdeEventStepper {
     }
     t_curr = t_prev + t_step;
     rhs_stage(pre_t[PRE ? S - 1 : 0], pre_p[PRE ? S - 1 : 0], d_curr);
-    n_rhs += S;
+    ++n_make;
     // pre-combined interpolant: cf_j = sum_i k_i bi[i][j] / t_step^(j-1)  (needs b_i(0) = 0: host-checked)
     t_slide = hist.t_look;
     const double inv = 1.0 / t_step;
@@ -818,7 +819,7 @@ struct DdeEventStepper {
 
   __device__ __forceinline__ int next_mode() {
     const bool more = t_curr < A.t1;
-    const bool limit = more && A.max_steps > 0 && (long long)n_steps >= A.max_steps;
+    const bool limit = more && n_steps >= step_limit;
     hist.status |= limit ? uint32_t(DFB_TRAJ_STEP_LIMIT) : 0u;
     return (more && !limit && !(hist.status & kPanicBits)) ? MODE_STEP : MODE_DONE;
   }
@@ -871,7 +872,7 @@ struct DdeEventStepper {
       trk_index[l] = 0;
     }
     n_steps = n_events = n_evlog = n_samples = n_iters = on_step_calls = 0u;
-    n_rhs = 0ull;
+    n_make = n_k0 = 0u;
     if (A.on_start_cb != DFB_CB_NONE) {  // events_on_start.eval_mut (solver.rs:289)
       RefMut m{&t_curr, p_curr, d_curr, t_prev, p_prev, &hist};
       Sys::callback(A.on_start_cb, m, prm, aux);
@@ -897,7 +898,7 @@ struct DdeEventStepper {
     }
     A.steps[gid] = n_steps;
     A.events[gid] = n_events;
-    A.rhs_evals[gid] = n_rhs;
+    A.rhs_evals[gid] = (unsigned long long)n_make * S + n_k0;
     A.status[gid] = st;
     if (A.locate_iters) A.locate_iters[gid] = n_iters;
     if (A.n_events) A.n_events[gid] = n_evlog;
@@ -912,6 +913,7 @@ struct DdeEventStepper {
     int ev_index = 0;
     uint32_t fired_mask = 0u;
     int parked_iters = 0;
+    step_limit = A.max_steps > 0 ? (A.max_steps >= 0xFFFFFFFFll ? 0xFFFFFFFFu : unsigned(A.max_steps)) : 0xFFFFFFFFu;
 
     while (true) {
       while (mode == MODE_DONE && !exhausted) {
@@ -980,7 +982,7 @@ struct DdeEventStepper {
             const double h_req = restep ? (ev_time - t_curr) : fmin(A.h, A.t1 - t_curr);
             if (t_prev == t_curr) {  // state.rs:97-98: make_step evaluates k[0] itself
               Sys::rhs(view_curr(), prm, d_curr);
-              ++n_rhs;
+              ++n_k0;
             }
             make_step(h_req);
             if (hist.status & kPanicBits) {
